@@ -1,0 +1,122 @@
+/*
+ * lfpsqp_b200.h -- C ABI of the B200-native LFPSQP hot path (liblfpsqp_b200.so).
+ *
+ * This is the drop-in boundary: the symbols a Julia maintainer binds with `ccall` in place of the pure-Julia
+ * hot path of LFPSQP.jl (the existing FFI style is src/la_helper.jl:22-28, :37-43: plain C symbols, arrays as
+ * Ptr{Float64}, status by integer).  Every array is dense, Float64, host memory unless the name ends in `_dev`.
+ * Matrices follow Julia's column-major convention at the boundary: an (n x B) batch is instance-major in memory
+ * (instance k occupies [k*n, (k+1)*n)).  The constraint Jacobian is held on the device as J (m x n) ROW-major,
+ * which is byte-identical to the reference's `Jct` (n x m column-major, src/optimize.jl:190).
+ *
+ * Julia closures cannot run on the device, so f / c! / d! and their derivatives are REGISTERED DEVICE FAMILIES
+ * (family id + parameter blob) -- the contract they implement is the one src/autodiff_generators.jl produces:
+ * grad!(g,x) (:7-9), jac!(Jc,cval,x) which also writes cval (:40-42), hess_lag_vec!(dest,src,x,lambda) (:80-104).
+ *
+ * Return codes: 0 ok; <0 argument errors mirroring the reference's error() calls; CUDA errors are mapped to
+ * LFPSQP_ERR_CUDA.  Message via lfpsqp_last_error().  Algorithmic failures are in-band per-instance flags.
+ * Calls block until results are in the caller's buffers.  One ctx per host thread (a ctx is not re-entrant).
+ */
+#ifndef LFPSQP_B200_H
+#define LFPSQP_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LFPSQP_OK 0
+#define LFPSQP_ERR_ARG (-1)        /* bad sizes: optimize.jl:19-21, :144-148 ; inequality_helper.jl:42-44 */
+#define LFPSQP_ERR_BOUNDS (-2)     /* "Infeasible: lower bounds cannot be greater than upper bounds" optimize.jl:160-162 */
+#define LFPSQP_ERR_FAMILY (-3)     /* unknown family / family does not support these sizes */
+#define LFPSQP_ERR_UNSUPPORTED (-4)/* beta>0 noise (optimize.jl:264-273), user callback (:432-434) */
+#define LFPSQP_ERR_CUDA (-5)
+#define LFPSQP_ERR_NOMEM (-6)
+#define LFPSQP_ERR_COMM (-7)
+
+/* LFPSQPParams, src/LFPSQP.jl:57-81 (same defaults: lfpsqp_default_params). disp/callback are host-side
+ * cosmetics of the reference and are ignored by the device path. */
+typedef struct {
+  double alpha, beta;
+  int64_t t_beta;
+  double s, sigma, eps_c, eps_f, eps_x, eps_kkt, eps_rank;
+  int64_t maxiter, maxiter_retract, maxiter_pcg;
+  double mu0;
+  int32_t disable_linesearch, do_project_retract, disp, linesearch /*0 armijo, 1 exact*/, do_newton;
+  int32_t _pad;
+  int64_t tn_maxiter;
+  double tn_kappa;
+  int64_t callback_period;
+} lfpsqp_params;
+
+/* TerminationCondition, src/LFPSQP.jl:37-43 */
+enum { LFPSQP_F_TOL = 0, LFPSQP_X_TOL = 1, LFPSQP_KKT_TOL = 2, LFPSQP_MAX_ITER = 3, LFPSQP_ARMIJO_ERROR = 4 };
+
+/* per-instance status bits (in-band; 0 = the path is the reference's path) */
+#define LFPSQP_ST_RANK_DEFICIENT 1 /* Cholesky of J W J' broke down: the reference would truncate the SVD (optimize.jl:297-302); we stop */
+#define LFPSQP_ST_NONFINITE 2
+
+/* TerminationInfo, src/LFPSQP.jl:45-51 : {Int32 enum, 3 x Float64, Int64}; the enum's padding carries status */
+typedef struct {
+  int32_t condition;
+  int32_t status;
+  double f_diff, step_diff, kkt_diff;
+  int64_t iter;
+} lfpsqp_term;
+
+/* optional per-instance counters (NULL to skip). flag_last = last line-search/retraction flag (linesearch.jl:32-89) */
+typedef struct {
+  int64_t projcg_iters, projcg_negcurv, armijo_trials, retract_outer, retract_pcg, pp_backtracks;
+  int64_t newton_accepted, factorizations, f_evals;
+  int64_t flag_last;
+} lfpsqp_stats;
+
+/* registered device families (the benchmark problem families of BASELINE.json + the reference's test systems) */
+enum {
+  LFPSQP_FAM_ROSENBROCK = 0, /* README.md:18-22; n=2, m=p=0; no params */
+  LFPSQP_FAM_README_EQ = 1,  /* README.md:41-54; f=x.x, c=x[1]-0.75; m=1 */
+  LFPSQP_FAM_README_INEQ = 2,/* README.md:57-76; f=coeff.x, d=x.x-1; p=1; params = coeff[n] per instance */
+  LFPSQP_FAM_THOMSON = 3,    /* n=3N, f=sum_{i<j} 1/|xi-xj|, c_i=|x_i|^2-1, m=N */
+  LFPSQP_FAM_DIAGQUAD = 4,   /* c_i = 1/2 sum_j Q_ij x_j^2 + A_i.x - b_i ; f = 1/2 sum_j w_j (x_j-xt_j)^2
+                                params = [Q (m x n row-major), A (m x n row-major), b(m), xt(n), w(n)] */
+  LFPSQP_FAM_SIN = 5,        /* test/test_retractions.jl:34-54: c_i = x[2i]-sin(x[2i-1]); f=1/2|x-t|^2; params=t[n] */
+  LFPSQP_FAM_BOXQUAD = 6,    /* f=|x-t|^2, optional c=a.x-b (m in {0,1}); params=[t(n), a(n), b] */
+  LFPSQP_FAM_COUNT = 7
+};
+
+typedef struct lfpsqp_ctx lfpsqp_ctx;
+
+const char *lfpsqp_version(void);
+void lfpsqp_default_params(lfpsqp_params *p);                      /* src/LFPSQP.jl:57-81 */
+int lfpsqp_ctx_create(int device, lfpsqp_ctx **out);               /* fails loudly (LFPSQP_ERR_CUDA) without a GPU */
+void lfpsqp_ctx_destroy(lfpsqp_ctx *ctx);
+const char *lfpsqp_last_error(lfpsqp_ctx *ctx);                    /* ctx may be NULL: last error of ctx_create */
+/* run on a caller-owned stream (e.g. torch's current stream) instead of the ctx's own; NULL restores it */
+int lfpsqp_ctx_set_stream(lfpsqp_ctx *ctx, void *cuda_stream);
+/* device time (ms, CUDA events on the launching stream) and launch count of the kernels of the last solve call */
+double lfpsqp_last_kernel_ms(lfpsqp_ctx *ctx);
+int64_t lfpsqp_last_launches(lfpsqp_ctx *ctx);
+
+/*
+ * Batched mode: B independent instances of optimize(f, c!, d!, x0, xl, xu, m, p, param)  (src/optimize.jl:83-85 and
+ * the methods it forwards to, :13-71, :88-104, :119-443), solved in lockstep on one GPU, one warp (or one thread for
+ * tiny unconstrained problems) per instance.
+ *   fam_params : per-instance parameter blobs, instance k at fam_params + k*fam_stride (fam_stride 0 = shared)
+ *   x0         : n x B ; xl, xu : n (shared by the batch) or NULL (= `nothing`)
+ *   x_out      : n x B ; obj_hist : H x B (first min(len,H) objective values) ; obj_len : B (iters+1)
+ *   lambda     : (m+p) x B (untruncated, optimize.jl:67-70) ; term : B ; stats : B or NULL
+ */
+int lfpsqp_solve_batched(lfpsqp_ctx *ctx, int family, int64_t n, int64_t m, int64_t p, int64_t B,
+                         const double *fam_params, int64_t fam_stride, const double *x0, const double *xl,
+                         const double *xu, const lfpsqp_params *params, double *x_out, double *obj_hist, int64_t H,
+                         int64_t *obj_len, double *lambda, lfpsqp_term *term, lfpsqp_stats *stats);
+/* same with every array already resident in device memory (xl/xu stay host: they are n doubles of setup data) */
+int lfpsqp_solve_batched_dev(lfpsqp_ctx *ctx, int family, int64_t n, int64_t m, int64_t p, int64_t B,
+                             const double *fam_params_dev, int64_t fam_stride, const double *x0_dev, const double *xl,
+                             const double *xu, const lfpsqp_params *params, double *x_out_dev, double *obj_hist_dev,
+                             int64_t H, int64_t *obj_len_dev, double *lambda_dev, lfpsqp_term *term_dev,
+                             lfpsqp_stats *stats_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,119 @@
+"""ctypes binding of liblfpsqp_b200.so -- exactly the C ABI of include/lfpsqp_b200.h (what Julia's ccall binds).
+
+There is no CPU fallback: a missing library or a missing GPU raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblfpsqp_b200.so")
+
+
+class CParams(C.Structure):  # lfpsqp_params == LFPSQPParams, src/LFPSQP.jl:57-81
+    _fields_ = [("alpha", C.c_double), ("beta", C.c_double), ("t_beta", C.c_int64), ("s", C.c_double),
+                ("sigma", C.c_double), ("eps_c", C.c_double), ("eps_f", C.c_double), ("eps_x", C.c_double),
+                ("eps_kkt", C.c_double), ("eps_rank", C.c_double), ("maxiter", C.c_int64),
+                ("maxiter_retract", C.c_int64), ("maxiter_pcg", C.c_int64), ("mu0", C.c_double),
+                ("disable_linesearch", C.c_int32), ("do_project_retract", C.c_int32), ("disp", C.c_int32),
+                ("linesearch", C.c_int32), ("do_newton", C.c_int32), ("_pad", C.c_int32),
+                ("tn_maxiter", C.c_int64), ("tn_kappa", C.c_double), ("callback_period", C.c_int64)]
+
+
+TERM_DTYPE = np.dtype([("condition", "<i4"), ("status", "<i4"), ("f_diff", "<f8"), ("step_diff", "<f8"),
+                       ("kkt_diff", "<f8"), ("iter", "<i8")])
+STATS_FIELDS = ("projcg_iters", "projcg_negcurv", "armijo_trials", "retract_outer", "retract_pcg", "pp_backtracks",
+                "newton_accepted", "factorizations", "f_evals", "flag_last")
+STATS_DTYPE = np.dtype([(k, "<i8") for k in STATS_FIELDS])
+
+EXPORTS = [
+    "lfpsqp_version", "lfpsqp_default_params", "lfpsqp_ctx_create", "lfpsqp_ctx_destroy", "lfpsqp_last_error",
+    "lfpsqp_ctx_set_stream", "lfpsqp_last_kernel_ms", "lfpsqp_last_launches", "lfpsqp_solve_batched",
+    "lfpsqp_solve_batched_dev",
+]
+
+_lib = None
+
+
+def load():
+    """Load the shared library (no GPU needed for this step)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("liblfpsqp_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                               "there is no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        lib.lfpsqp_version.restype = C.c_char_p
+        lib.lfpsqp_last_error.restype = C.c_char_p
+        lib.lfpsqp_last_error.argtypes = [C.c_void_p]
+        lib.lfpsqp_last_kernel_ms.restype = C.c_double
+        lib.lfpsqp_last_kernel_ms.argtypes = [C.c_void_p]
+        lib.lfpsqp_last_launches.restype = C.c_int64
+        lib.lfpsqp_last_launches.argtypes = [C.c_void_p]
+        lib.lfpsqp_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        lib.lfpsqp_ctx_destroy.argtypes = [C.c_void_p]
+        lib.lfpsqp_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        P = C.c_void_p
+        I = C.c_int64
+        sig = [P, C.c_int, I, I, I, I, P, I, P, P, P, P, P, P, I, P, P, P, P]
+        lib.lfpsqp_solve_batched.argtypes = sig
+        lib.lfpsqp_solve_batched_dev.argtypes = sig
+        _lib = lib
+    return _lib
+
+
+class LFPSQPError(RuntimeError):
+    """Mirrors the reference's error() exceptions (optimize.jl:19-21, :144-148, :160-162)."""
+
+
+class Context:
+    """One lfpsqp_ctx (one GPU, one host thread)."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.lfpsqp_ctx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise LFPSQPError(self.lib.lfpsqp_last_error(None).decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lfpsqp_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != 0:
+            raise LFPSQPError("%s (rc=%d)" % (self.lib.lfpsqp_last_error(self.h).decode(), rc))
+
+    def set_stream(self, cuda_stream_ptr):
+        self.check(self.lib.lfpsqp_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    @property
+    def last_kernel_ms(self):
+        return self.lib.lfpsqp_last_kernel_ms(self.h)
+
+    @property
+    def last_launches(self):
+        return self.lib.lfpsqp_last_launches(self.h)
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+def ptr(a):
+    """host numpy array -> void* (None -> NULL)"""
+    return None if a is None else C.c_void_p(a.ctypes.data)

@@ -1,0 +1,30 @@
+// ctx.h -- the library context behind the opaque lfpsqp_ctx handle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/lfpsqp_b200.h"
+
+struct LargeState;  // large-n mode workspace (large.cu)
+
+struct lfpsqp_ctx {
+  int device = 0, sm_count = 148, smem_optin = 232448;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  unsigned long long *work_counter = nullptr;
+  double last_ms = 0.0;
+  int64_t last_launches = 0;
+  int last_cfg_warps = 0, last_cfg_grid = 0, last_cfg_smem = 0, last_cfg_resident = 0;
+  std::string err;
+  std::vector<void *> bufs;  // grow-only device arena, one slot per role (no allocation inside solve loops)
+  std::vector<size_t> caps;
+  LargeState *large = nullptr;
+
+  int fail(int code, const char *fmt, ...);
+  int cuda_fail(cudaError_t e, const char *what);
+  void *arena(int slot, size_t bytes);
+};
+
+void lfpsqp_large_release(lfpsqp_ctx *c);

@@ -1,0 +1,135 @@
+"""GPU parity tests (batched mode): CUDA path through the C ABI vs the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from tests.parity import compare_batch, fmt
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    import lfpsqp.jl_b200 as L
+    L.default_context(0)  # raises loudly when the CUDA library or the GPU is missing
+    return L
+
+
+def _require(res, all_frac=1.0):
+    print(fmt(res))
+    assert res["status_nonzero"] == 0
+    assert res["all_ok_frac"] >= all_frac, fmt(res)
+
+
+def test_rosenbrock_readme_golden(L):
+    # /root/reference/README.md:31-37 through the public API
+    fam = L.families.rosenbrock()
+    x, obj, lam, info = L.optimize(fam.f, np.zeros(2))
+    assert info.condition == L.TerminationCondition.f_tol and info.iter == 17
+    assert info.f_diff == pytest.approx(1.0898882046786806e-7, rel=1e-8)
+    assert info.step_diff == pytest.approx(0.0007384068067118611, rel=1e-8)
+    assert info.kkt_diff == pytest.approx(4.332627751789361e-5, rel=1e-8)
+    assert len(obj) == 18 and lam.size == 0
+
+
+def test_rosenbrock_batch_vs_oracle(L, oracle):
+    rng = np.random.default_rng(0)
+    B = 4096
+    x0 = rng.uniform(-2, 2, (B, 2)); x0[0] = 0.0
+    fam = L.families.rosenbrock()
+    gpu = L.optimize_batched(fam.f, x0, history=128)
+    orc = oracle.optimize_batched("rosenbrock", 2, 0, 0, x0, H=128, nthreads=8)
+    _require(compare_batch(gpu, orc, 2, "rosenbrock"), 0.995)
+
+
+def test_readme_equality(L, oracle):
+    fam = L.families.readme_equality(50)
+    x, obj, lam, info = L.optimize(fam.f, fam.c, np.ones(50), 1)
+    ox, oobj, olam, ot, _ = oracle.optimize("readme_eq", 50, 1, 0, np.ones(50))
+    assert info.condition == ot["condition"] and info.iter == ot["iter"] == 1
+    assert np.linalg.norm(x - ox) <= 1e-8 * np.linalg.norm(ox)
+    assert abs(obj[-1] - oobj[-1]) <= 1e-10 * abs(oobj[-1])
+    assert lam[0] == pytest.approx(olam[0], rel=1e-8)
+    assert info.f_diff == pytest.approx(49.437499625000314, rel=1e-12)
+    assert info.step_diff == pytest.approx(7.0044628541380805, rel=1e-12)
+
+
+def test_readme_inequality_batch_vs_oracle(L, oracle):
+    rng = np.random.default_rng(1)
+    B, n = 512, 50
+    co = rng.standard_normal((B, n))
+    inf = np.inf * np.ones(n)
+    fam = L.families.readme_inequality(co)
+    gpu = L.optimize_batched(fam.f, None, fam.d, np.zeros((B, n)), -inf, inf, 0, 1)
+    orc = oracle.optimize_batched("readme_ineq", n, 0, 1, np.zeros((B, n)), xl=-inf, xu=inf, fam_params=co,
+                                  fam_stride=n, nthreads=8)
+    res = compare_batch(gpu, orc, n, "readme_ineq")
+    _require(res, 0.99)
+    # known solution x* = -coeff/|coeff|
+    nc = np.linalg.norm(co, axis=1)
+    assert np.max(np.linalg.norm(gpu[0] + co / nc[:, None], axis=1)) < 1e-4
+
+
+@pytest.mark.parametrize("m", [0, 1])
+def test_bounds_boxquad_vs_oracle(L, oracle, m):
+    rng = np.random.default_rng(2 + m)
+    B, n = 256, 12
+    xl = np.r_[-np.inf * np.ones(3), -0.5 * np.ones(3), -np.inf * np.ones(3), -0.3 * np.ones(3)]
+    xu = np.r_[np.inf * np.ones(6), 0.4 * np.ones(3), 0.6 * np.ones(3)]
+    t = 2 * rng.standard_normal((B, n))
+    fam = L.families.boxquad(t, a=np.ones(n) if m else None, b=3.0)
+    x0 = np.tile(np.clip(np.zeros(n), xl, xu) + (0.25 if m else 0.0), (B, 1))
+    if m:
+        gpu = L.optimize_batched(fam.f, fam.c, x0, xl, xu, 1)
+    else:
+        gpu = L.optimize_batched(fam.f, None, x0, xl, xu, 0)
+    orc = oracle.optimize_batched("boxquad", n, m, 0, x0, xl=xl, xu=xu, fam_params=fam.params,
+                                  fam_stride=fam.params.shape[1], nthreads=8)
+    _require(compare_batch(gpu, orc, n, "boxquad m=%d" % m), 0.97)
+
+
+@pytest.mark.parametrize("nr", [False, True])
+def test_sin_system_vs_oracle(L, oracle, nr):
+    rng = np.random.default_rng(5)
+    B, n, m = 128, 24, 6
+    t = rng.standard_normal((B, n))
+    x0 = np.zeros((B, n))
+    fam = L.families.sin_system(n, m, t)
+    prm = L.LFPSQPParams(do_project_retract=not nr)
+    gpu = L.optimize_batched(fam.f, fam.c, x0, m, prm)
+    oprm = oracle.default_params(do_project_retract=0 if nr else 1)
+    orc = oracle.optimize_batched("sin", n, m, 0, x0, fam_params=t, fam_stride=n, params=oprm, nthreads=8)
+    _require(compare_batch(gpu, orc, n, "sin nr=%s" % nr), 0.97)
+
+
+def test_thomson_small_vs_oracle(L, oracle):
+    rng = np.random.default_rng(6)
+    B, npts = 64, 12
+    x0 = rng.standard_normal((B, npts, 3)); x0 /= np.linalg.norm(x0, axis=2, keepdims=True)
+    x0 = x0.reshape(B, 3 * npts)
+    fam = L.families.thomson(npts)
+    gpu = L.optimize_batched(fam.f, fam.c, x0, npts)
+    orc = oracle.optimize_batched("thomson", 3 * npts, npts, 0, x0, nthreads=8)
+    _require(compare_batch(gpu, orc, 3 * npts, "thomson12"), 0.9)
+
+
+def test_diagquad_small_vs_oracle(L, oracle):
+    rng = np.random.default_rng(7)
+    B, n, m = 64, 64, 4
+    Q = rng.standard_normal((m, n)) / np.sqrt(n); A = rng.standard_normal((m, n)) / np.sqrt(n)
+    xt = rng.standard_normal(n); w = np.exp(rng.uniform(0, np.log(100.0), n))
+    xs = rng.standard_normal(n)
+    b = 0.5 * Q @ (xs * xs) + A @ xs
+    x0 = np.tile(xs, (B, 1))
+    fam = L.families.diagquad(Q, A, b, xt, w)
+    # different targets per instance are not needed: perturb the (feasible) start along the batch instead
+    gpu = L.optimize_batched(fam.f, fam.c, x0, m)
+    orc = oracle.optimize_batched("diagquad", n, m, 0, x0, fam_params=fam.params, fam_stride=0, nthreads=8)
+    _require(compare_batch(gpu, orc, n, "diagquad"), 0.95)
+
+
+def test_error_conventions(L):
+    fam = L.families.boxquad(np.zeros(4))
+    with pytest.raises(L.LFPSQPError):   # optimize.jl:160-162
+        L.optimize(fam.f, None, np.zeros(4), np.ones(4), -np.ones(4), 0)
+    with pytest.raises(L.LFPSQPError):   # optimize.jl:144-148
+        L.optimize(fam.f, None, np.zeros(4), np.ones(3), np.ones(3), 0)
