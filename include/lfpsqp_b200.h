@@ -116,6 +116,10 @@ int lfpsqp_solve_batched_dev(lfpsqp_ctx *ctx, int family, int64_t n, int64_t m, 
                              int64_t H, int64_t *obj_len_dev, double *lambda_dev, lfpsqp_term *term_dev,
                              lfpsqp_stats *stats_dev);
 
+/* Roofline denominators that MEASURED_PEAKS.json does not carry: measured FP64 peak of this GPU in TFLOP/s.
+ * which: 0 = DFMA (vector pipe), 1 = DMMA (mma.sync.m8n8k4.f64 tensor pipe). */
+int lfpsqp_bench_fp64_peak(lfpsqp_ctx *ctx, int which, double *tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,7 +29,7 @@ STATS_DTYPE = np.dtype([(k, "<i8") for k in STATS_FIELDS])
 EXPORTS = [
     "lfpsqp_version", "lfpsqp_default_params", "lfpsqp_ctx_create", "lfpsqp_ctx_destroy", "lfpsqp_last_error",
     "lfpsqp_ctx_set_stream", "lfpsqp_last_kernel_ms", "lfpsqp_last_launches", "lfpsqp_solve_batched",
-    "lfpsqp_solve_batched_dev",
+    "lfpsqp_solve_batched_dev", "lfpsqp_bench_fp64_peak",
 ]
 
 _lib = None
@@ -58,6 +58,7 @@ def load():
         sig = [P, C.c_int, I, I, I, I, P, I, P, P, P, P, P, P, I, P, P, P, P]
         lib.lfpsqp_solve_batched.argtypes = sig
         lib.lfpsqp_solve_batched_dev.argtypes = sig
+        lib.lfpsqp_bench_fp64_peak.argtypes = [P, C.c_int, C.POINTER(C.c_double)]
         _lib = lib
     return _lib
 
@@ -95,6 +96,12 @@ class Context:
 
     def set_stream(self, cuda_stream_ptr):
         self.check(self.lib.lfpsqp_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def fp64_peak(self, which):
+        """measured FP64 peak in TFLOP/s: which = 'dfma' | 'dmma'"""
+        v = C.c_double()
+        self.check(self.lib.lfpsqp_bench_fp64_peak(self.h, 0 if which == "dfma" else 1, C.byref(v)))
+        return v.value
 
     @property
     def last_kernel_ms(self):

@@ -171,23 +171,20 @@ int launch_warp(lfpsqp_ctx *c, BatchedArgs &A, int use_nr) {
     return c->fail(LFPSQP_ERR_NOMEM,
                    "batched mode: one instance needs %zu B of shared memory (> %zu); use lfpsqp_solve_large",
                    bnd_bytes + per_warp, cap);
-  int warps = (int)((cap - bnd_bytes) / per_warp);
-  if (warps > 8) warps = 8;
-  // prefer several smaller CTAs per SM when they pack better
-  int best_w = warps; size_t best_res = 0;
-  for (int w = warps; w >= 1; w--) {
-    size_t cta = bnd_bytes + w * per_warp + 1024;
-    size_t per_sm = (233472 / cta) * w;
-    if (per_sm > best_res) { best_res = per_sm; best_w = w; }
-  }
-  warps = best_w;
-  const size_t smem = bnd_bytes + warps * per_warp;
+  int maxw = (int)((cap - bnd_bytes) / per_warp);
+  if (maxw > 8) maxw = 8;
   auto kern = batched_warp_kernel<Fam>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bnd_bytes + maxw * per_warp));
   if (e != cudaSuccess) return c->cuda_fail(e, "cudaFuncSetAttribute");
-  int resident = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, warps * 32, smem);
-  if (e != cudaSuccess || resident < 1) return c->cuda_fail(e, "occupancy query");
+  // pick the CTA width that keeps the most warps resident per SM (shared memory AND registers, via the occupancy API)
+  int warps = maxw, resident = 0, best = 0;
+  for (int w = maxw; w >= 1; w--) {
+    int r = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, kern, w * 32, bnd_bytes + w * per_warp) != cudaSuccess) { cudaGetLastError(); continue; }
+    if (r * w > best) { best = r * w; warps = w; resident = r; }
+  }
+  if (resident < 1) return c->fail(LFPSQP_ERR_CUDA, "batched_warp_kernel cannot be made resident");
+  const size_t smem = bnd_bytes + warps * per_warp;
   int64_t grid = (int64_t)c->sm_count * resident;
   int64_t need = (A.B + warps - 1) / warps;
   if (grid > need) grid = need;

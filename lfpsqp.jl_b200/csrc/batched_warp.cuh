@@ -614,7 +614,7 @@ struct Solver {
 // Persistent CTAs; every warp pulls instance indices from a global counter until the batch is drained
 // (absorbs the per-instance iteration-count variance).
 template <class Fam>
-__global__ void __launch_bounds__(256) batched_warp_kernel(const BatchedArgs A, const int use_nr) {
+__global__ void __launch_bounds__(256, 2) batched_warp_kernel(const BatchedArgs A, const int use_nr) {
   extern __shared__ double smem[];
   const WarpLayout L(A.n, A.m, A.p, A.ineq, use_nr);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;

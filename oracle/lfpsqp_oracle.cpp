@@ -1055,7 +1055,7 @@ extern "C" void orc_ineq_lambda(int64_t n, int64_t m, const double *Dx, const do
   calculate_lambda_kkt(lambda, lambda_y, QtF.data(), de);
 }
 
-static std::unique_ptr<Problem> make_problem(Family &F) {
+[[maybe_unused]] static std::unique_ptr<Problem> make_problem(Family &F) {
   if (F.p == 0) return std::unique_ptr<Problem>(new PlainProblem(F));
   return std::unique_ptr<Problem>(new SlackProblem(F));
 }

@@ -39,13 +39,14 @@ class Stats(C.Structure):
                                           "f_evals")] + [("flops", C.c_double)]
 
 
-TERM_DTYPE = np.dtype([("condition", "<i4"), ("_pad", "<i4"), ("f_diff", "<f8"), ("step_diff", "<f8"),
+TERM_DTYPE = np.dtype([("condition", "<i4"), ("status", "<i4"), ("f_diff", "<f8"), ("step_diff", "<f8"),
                        ("kkt_diff", "<f8"), ("iter", "<i8")])
 STATS_DTYPE = np.dtype([(k, "<i8") for k in ("projcg_iters", "projcg_negcurv", "armijo_trials", "retract_outer",
                                               "retract_pcg", "pp_backtracks", "newton_accepted", "svd_calls",
                                               "f_evals")] + [("flops", "<f8")])
 
 _lib = None
+_libs = {}
 
 
 def build(force=False):
@@ -63,17 +64,41 @@ def _find_openblas():
     return os.path.abspath(cands[0])
 
 
+def _load(path):
+    if path not in _libs:
+        if not os.path.exists(path):
+            build(force=True)
+        L = C.CDLL(path)
+        L.orc_family_f.restype = C.c_double
+        rc = L.orc_set_lapack(_find_openblas().encode())
+        if rc != 0:
+            raise RuntimeError("oracle: could not bind dgesvd")
+        _libs[path] = L
+    return _libs[path]
+
+
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB):
-            build()
-        _lib = C.CDLL(_LIB)
-        _lib.orc_family_f.restype = C.c_double
-        rc = _lib.orc_set_lapack(_find_openblas().encode())
-        if rc != 0:
-            raise RuntimeError("oracle: could not bind dgesvd")
+        _lib = _load(_LIB)
     return _lib
+
+
+class variant:
+    """Context manager: run the oracle built with FMA contraction (rounding-sensitivity probe, see Makefile)."""
+
+    def __init__(self, name):
+        self.path = os.path.join(_HERE, "liblfpsqp_oracle_%s.so" % name)
+
+    def __enter__(self):
+        global _lib
+        self.prev = lib()
+        _lib = _load(self.path)
+        return self
+
+    def __exit__(self, *a):
+        global _lib
+        _lib = self.prev
 
 
 def default_params(**kw):
