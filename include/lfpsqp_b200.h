@@ -116,6 +116,36 @@ int lfpsqp_solve_batched_dev(lfpsqp_ctx *ctx, int family, int64_t n, int64_t m, 
                              int64_t H, int64_t *obj_len_dev, double *lambda_dev, lfpsqp_term *term_dev,
                              lfpsqp_stats *stats_dev);
 
+/*
+ * Large-n mode: ONE instance with a dense m x n constraint Jacobian, host-orchestrated whole-GPU kernels
+ * (FP64 DMMA Gram + blocked Cholesky replace ksvd!, src/la_helper.jl:8-34 / optimize.jl:291-293; streaming passes over
+ * J replace kgemv!, la_helper.jl:36-44).  Families: LFPSQP_FAM_DIAGQUAD, LFPSQP_FAM_THOMSON.  No finite bounds yet.
+ * Column sharding: with a communicator (lfpsqp_comm_init) rank g owns columns [col0, col0+n_loc) of J and the same
+ * entries of every n-vector; m-vectors and the m x m factor are replicated; only the Gram, the m-vector J v and the
+ * CG scalars are all-reduced.  Without a communicator col0 = 0, n_loc = n.
+ */
+/* optimize(f, c!, x0, xl, xu, m, param) for one large instance on one GPU (fam_params, x0: host; xl/xu NULL or +-Inf) */
+int lfpsqp_solve_large(lfpsqp_ctx *ctx, int family, int64_t n, int64_t m, const double *fam_params, const double *x0,
+                       const double *xl, const double *xu, const lfpsqp_params *params, double *x_out, double *obj_hist,
+                       int64_t H, int64_t *obj_len, double *lambda, lfpsqp_term *term, lfpsqp_stats *stats);
+/* two-step form: bind the (sharded) problem once, then solve / probe it.  DIAGQUAD params = this rank's shard
+ * [Q_loc (m x n_loc row-major), A_loc (m x n_loc), b (m), xt_loc (n_loc), w_loc (n_loc)], host or device memory. */
+int lfpsqp_large_setup(lfpsqp_ctx *ctx, int family, int64_t n_global, int64_t m, int64_t col0, int64_t n_loc,
+                       const double *params, int params_on_device);
+int lfpsqp_large_solve(lfpsqp_ctx *ctx, const double *x0_loc, const lfpsqp_params *params, double *x_out_loc,
+                       double *obj_hist, int64_t H, int64_t *obj_len, double *lambda, lfpsqp_term *term,
+                       lfpsqp_stats *stats);
+/* unit-level ops mirroring the reference functions one to one (host buffers; outputs may be NULL):
+ *   factor  : J = jac(x); G = J J' (m x m row-major, lower triangle valid), L = chol(G), Linv = L^-1   [ksvd!]
+ *   project : v - J'(J J')^-1 J v and lambda = (J J')^-1 J v with the cached factor                    [kgemv! x2, optimize.jl:306-307, :333-343]
+ *   projcg  : projcg! (src/projcg.jl:40-121) at x with multipliers lam on b = P(-grad f(x)), c = 0; status:
+ *             1 converged, 2 negative curvature, 3 rg<=0, 4 iteration limit; ms = device time of the loop */
+int lfpsqp_large_factor(lfpsqp_ctx *ctx, const double *x_loc, double *G_out, double *L_out, double *Linv_out,
+                        int *rank_deficient, double *gram_ms);
+int lfpsqp_large_project(lfpsqp_ctx *ctx, const double *v_loc, double *v_out_loc, double *lambda_out);
+int lfpsqp_large_projcg(lfpsqp_ctx *ctx, const double *x_loc, const double *lam, double tol, int64_t maxit, int chunk,
+                        double *sol_out_loc, int64_t *iters, double *nr, int *status, double *ms);
+
 /* Roofline denominators that MEASURED_PEAKS.json does not carry: measured FP64 peak of this GPU in TFLOP/s.
  * which: 0 = DFMA (vector pipe), 1 = DMMA (mma.sync.m8n8k4.f64 tensor pipe). */
 int lfpsqp_bench_fp64_peak(lfpsqp_ctx *ctx, int which, double *tflops);

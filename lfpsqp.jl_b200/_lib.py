@@ -29,7 +29,8 @@ STATS_DTYPE = np.dtype([(k, "<i8") for k in STATS_FIELDS])
 EXPORTS = [
     "lfpsqp_version", "lfpsqp_default_params", "lfpsqp_ctx_create", "lfpsqp_ctx_destroy", "lfpsqp_last_error",
     "lfpsqp_ctx_set_stream", "lfpsqp_last_kernel_ms", "lfpsqp_last_launches", "lfpsqp_solve_batched",
-    "lfpsqp_solve_batched_dev", "lfpsqp_bench_fp64_peak",
+    "lfpsqp_solve_batched_dev", "lfpsqp_bench_fp64_peak", "lfpsqp_solve_large", "lfpsqp_large_setup",
+    "lfpsqp_large_solve", "lfpsqp_large_factor", "lfpsqp_large_project", "lfpsqp_large_projcg",
 ]
 
 _lib = None
@@ -59,6 +60,12 @@ def load():
         lib.lfpsqp_solve_batched.argtypes = sig
         lib.lfpsqp_solve_batched_dev.argtypes = sig
         lib.lfpsqp_bench_fp64_peak.argtypes = [P, C.c_int, C.POINTER(C.c_double)]
+        lib.lfpsqp_solve_large.argtypes = [P, C.c_int, I, I, P, P, P, P, P, P, P, I, P, P, P, P]
+        lib.lfpsqp_large_setup.argtypes = [P, C.c_int, I, I, I, I, P, C.c_int]
+        lib.lfpsqp_large_solve.argtypes = [P, P, P, P, P, I, P, P, P, P]
+        lib.lfpsqp_large_factor.argtypes = [P, P, P, P, P, P, P]
+        lib.lfpsqp_large_project.argtypes = [P, P, P, P]
+        lib.lfpsqp_large_projcg.argtypes = [P, P, P, C.c_double, I, C.c_int, P, P, P, P, P]
         _lib = lib
     return _lib
 

@@ -1,3 +1,745 @@
-// large.cu -- large-n mode (column-sharded J, host-orchestrated streams/graphs).  Filled in below.
+// large.cu -- large-n mode: one instance, dense J (m x n) column-sharded over the ranks, host-orchestrated.
+//
+// The reference's driver (src/optimize.jl:119-443) runs here on the host as stream orchestration; every O(n) /
+// O(mn) / O(m^2 n) operation is a hand-written kernel (large_gemm.cuh, large_kernels.cuh, large_families.cuh).
+// Inner loops (projcg!, pcg!) are device-predicated: their kernels test ctrl->status, so iterations are enqueued
+// in chunks and the host reads the control block once per chunk.
+// Bounds (the 2n-variable embedding) are not supported in this mode yet: BASELINE configs C4/C5 have none.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+
 #include "ctx.h"
-void lfpsqp_large_release(lfpsqp_ctx *) {}
+#include "large_gemm.cuh"
+#include "large_kernels.cuh"
+#include "large_families.cuh"
+#include "large_state.h"
+
+using namespace lfpsqp;
+
+#define CK(call)                                                        \
+  do {                                                                  \
+    cudaError_t e__ = (call);                                           \
+    if (e__ != cudaSuccess) return c->cuda_fail(e__, #call);            \
+  } while (0)
+
+static inline int64_t up2(int64_t v) { return (v + 1) & ~(int64_t)1; }
+
+// ------------------------------------------------------------------ small launch helpers
+template <class F>
+static void vec(LargeState &S, int64_t n, F f, int s0 = 0, int nsum = 0, int domax = 0) {
+  vec_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, f, S.gpart, s0, nsum, domax);
+}
+static void finalize(LargeState &S, unsigned summask, unsigned maxmask) {
+  finalize_kernel<<<1, 256, 0, S.stream>>>(S.gpart, S.vgrid, summask, maxmask, S.ctrl);
+  S.launches++;
+  if (S.world > 1) comm_allreduce_scalars(S, summask, maxmask);
+}
+static int read_ctrl(lfpsqp_ctx *c, LargeState &S) {
+  CK(cudaMemcpyAsync(S.hctrl, S.ctrl, sizeof(LargeCtrl), cudaMemcpyDeviceToHost, S.stream));
+  CK(cudaStreamSynchronize(S.stream));
+  return 0;
+}
+static void write_ctrl_fields(LargeState &S) {  // push the host copy (tolerances, limits, statuses) to the device
+  cudaMemcpyAsync(S.ctrl, S.hctrl, sizeof(LargeCtrl), cudaMemcpyHostToDevice, S.stream);
+}
+
+// C (op)= A B' with optional split-K through S.gemm_ws
+static void gemm_nt(LargeState &S, int M, int N, int K, const double *A, int64_t lda, const double *B, int64_t ldb, double *C,
+                    int64_t ldc, int mode, int lower) {
+  if (M <= 0 || N <= 0) return;
+  const bool narrow = (N <= 64);
+  const int BN = narrow ? 64 : 128;
+  dim3 grid((N + BN - 1) / BN, (M + GM_BM - 1) / GM_BM, 1);
+  int tiles = grid.x * grid.y;
+  if (lower) tiles = (tiles + grid.y) / 2;
+  int ksplit = 1;
+  if (mode != GEMM_SUB && tiles * 2 <= S.sm_count && K >= 1024) {
+    ksplit = std::min(std::min(16, S.sm_count / tiles), K / 256);
+    while (ksplit > 1 && (size_t)ksplit * M * N * 8 > S.gemm_ws_bytes) ksplit--;
+    if (ksplit < 1) ksplit = 1;
+  }
+  if (ksplit == 1) {
+    if (narrow) dgemm_nt_kernel<64><<<grid, 256, dgemm_smem_bytes<64>(), S.stream>>>(M, N, K, A, lda, B, ldb, C, ldc, mode, lower, 1, 0);
+    else dgemm_nt_kernel<128><<<grid, 256, dgemm_smem_bytes<128>(), S.stream>>>(M, N, K, A, lda, B, ldb, C, ldc, mode, lower, 1, 0);
+    S.launches++;
+  } else {
+    grid.z = ksplit;
+    const int64_t stride = (int64_t)M * N;
+    if (narrow) dgemm_nt_kernel<64><<<grid, 256, dgemm_smem_bytes<64>(), S.stream>>>(M, N, K, A, lda, B, ldb, S.gemm_ws, N, GEMM_ASSIGN, lower, ksplit, stride);
+    else dgemm_nt_kernel<128><<<grid, 256, dgemm_smem_bytes<128>(), S.stream>>>(M, N, K, A, lda, B, ldb, S.gemm_ws, N, GEMM_ASSIGN, lower, ksplit, stride);
+    const double *ws = S.gemm_ws;
+    const double sgn = (mode == GEMM_ASSIGN_NEG) ? -1.0 : 1.0;
+    const int lo = lower;
+    vec(S, stride, [=] __device__(int64_t e, double *) {
+      int r = (int)(e / N), cc = (int)(e % N);
+      if (lo && (r / GM_BM) * GM_BM + GM_BM <= (cc / BN) * BN) return;   // tile was skipped
+      double s = 0.0;
+      for (int z = 0; z < ksplit; z++) s += ws[(int64_t)z * stride + e];
+      C[(int64_t)r * ldc + cc] = sgn * s;
+    });
+    S.launches += 2;
+  }
+}
+
+static void rows_dot(LargeState &S, const double *Jm, int64_t ld, int m, int64_t ncols, const double *v, double *t, int pred) {
+  if (m <= 0) return;
+  if (m >= 8 * S.sm_count) rows_dot_kernel<4><<<(m + 3) / 4, 256, 0, S.stream>>>(Jm, ld, m, ncols, v, t, S.ctrl, pred);
+  else if (m >= 2 * S.sm_count) rows_dot_kernel<2><<<(m + 1) / 2, 256, 0, S.stream>>>(Jm, ld, m, ncols, v, t, S.ctrl, pred);
+  else rows_dot_kernel<1><<<m, 256, 0, S.stream>>>(Jm, ld, m, ncols, v, t, S.ctrl, pred);
+  S.launches++;
+}
+static void cols_dot(LargeState &S, const double *Jm, int64_t ld, int m, int64_t ncols, const double *u, int pred) {
+  if (m <= 0) return;
+  dim3 grid((unsigned)((ncols + 511) / 512), S.nsplit);
+  cols_dot_kernel<<<grid, 256, S.rows_per_split * sizeof(double), S.stream>>>(Jm, ld, m, ncols, u, S.cpart, S.rows_per_split, S.ctrl, pred);
+  S.launches++;
+}
+// u = (J J')^-1 t through the cached factor: y = L^-1 t ; u = L^-T y
+static void gram_solve(LargeState &S, const double *t, double *u, double *u_copy, int pred) {
+  const int m = S.m;
+  tri_gemv_kernel<<<(m + 7) / 8, 256, m * sizeof(double), S.stream>>>(S.Linv, S.ldm, m, t, S.ty, 0, nullptr, S.ctrl, pred);
+  tri_gemv_kernel<<<(m + 7) / 8, 256, m * sizeof(double), S.stream>>>(S.XT, S.ldm, m, S.ty, u, 1, u_copy, S.ctrl, pred);
+  S.launches += 2;
+}
+
+// ------------------------------------------------------------------ family dispatch (device callbacks, whole-GPU kernels)
+static void fam_f(LargeState &S, const double *x) {  // -> gpart slot 0 (sum); caller finalizes s[0]
+  if (S.family == LFPSQP_FAM_DIAGQUAD) {
+    const double *xt = S.p_xt, *w = S.p_w;
+    vec(S, S.n_loc, [=] __device__(int64_t j, double *acc) { double t = x[j] - xt[j]; acc[0] += 0.5 * w[j] * t * t; }, 0, 1);
+  } else {
+    int np = (int)(S.n / 3);
+    thomson_pair_kernel<0><<<(np + 255) / 256, 256, 0, S.stream>>>(np, x, nullptr, nullptr, nullptr, S.gpart, 0, S.ctrl, 0);
+    // the pair kernel wrote (np+255)/256 partials; zero the rest of the slot so that finalize's fixed np is right
+    int used = (np + 255) / 256; double *gp = S.gpart; int vg = S.vgrid;
+    if (used < vg) vec(S, vg - used, [=] __device__(int64_t e, double *) { gp[used + e] = 0.0; });
+  }
+  S.launches++; S.f_evals++;
+}
+static void fam_grad(LargeState &S, double *g, const double *x) {
+  if (S.family == LFPSQP_FAM_DIAGQUAD) {
+    const double *xt = S.p_xt, *w = S.p_w;
+    vec(S, S.n_loc, [=] __device__(int64_t j, double *) { g[j] = w[j] * (x[j] - xt[j]); });
+  } else {
+    int np = (int)(S.n / 3);
+    thomson_pair_kernel<1><<<(np + 255) / 256, 256, 0, S.stream>>>(np, x, nullptr, nullptr, g, nullptr, 0, S.ctrl, 0);
+  }
+  S.launches++;
+}
+// cval = c(x); with Jout also the Jacobian (jac! writes both, autodiff_generators.jl:40-42)
+static void fam_c_jac(LargeState &S, double *Jout, double *cval, const double *x) {
+  const int m = S.m;
+  if (S.family == LFPSQP_FAM_DIAGQUAD) {
+    if (Jout) dq_rows_kernel<2, true><<<(m + 1) / 2, 256, 0, S.stream>>>(S.p_Q, S.p_A, S.ldj, m, S.n_loc, x, Jout, cval);
+    else dq_rows_kernel<2, false><<<(m + 1) / 2, 256, 0, S.stream>>>(S.p_Q, S.p_A, S.ldj, m, S.n_loc, x, nullptr, cval);
+    if (S.world > 1) comm_allreduce(S, cval, m);
+    const double *b = S.p_b;
+    vec(S, m, [=] __device__(int64_t i, double *) { cval[i] -= b[i]; });
+    S.launches += 2;
+  } else {
+    if (Jout) cudaMemsetAsync(Jout, 0, (size_t)m * S.ldj * sizeof(double), S.stream);  // dense-treated, as the reference
+    thomson_c_kernel<<<(m + 255) / 256, 256, 0, S.stream>>>(m, x, cval, Jout, S.ldj);
+    S.launches += 2;
+  }
+}
+// per outer iteration: whatever of the Lagrangian Hessian depends only on (x, lambda)
+static void fam_hess_prepare(LargeState &S, const double *x, const double *lam) {
+  (void)x;
+  if (S.family == LFPSQP_FAM_DIAGQUAD) {  // hdiag = w + Q' lambda : one pass over Q
+    cols_dot(S, S.p_Q, S.ldj, S.m, S.n_loc, lam, 0);
+    const double *cp = S.cpart, *w = S.p_w; double *hd = S.hdiag; int ns = S.nsplit; int64_t n = S.n_loc;
+    vec(S, n, [=] __device__(int64_t j, double *) {
+      double s = w[j];
+      for (int k = 0; k < ns; k++) s += cp[(int64_t)k * n + j];
+      hd[j] = s;
+    });
+    S.launches++;
+  }
+}
+// dest = H src, partial src.dest -> loop-partial slot 0 ; returns the number of partials written
+static int fam_hess(LargeState &S, double *dest, const double *src, const double *x, const double *lam, int pred) {
+  if (S.family == LFPSQP_FAM_DIAGQUAD) {
+    const double *hd = S.hdiag; const LargeCtrl *ctrl = S.ctrl; double *lp = S.lp;
+    // predicated elementwise kernel with the d.Ad partial
+    hess_diag_kernel<<<S.vgrid, 256, 0, S.stream>>>(S.n_loc, hd, src, dest, lp, ctrl, pred);
+    S.launches++;
+    return S.vgrid;
+  } else {
+    int np = (int)(S.n / 3);
+    thomson_pair_kernel<2><<<(np + 255) / 256, 256, 0, S.stream>>>(np, x, src, lam, dest, S.lp, 0, S.ctrl, pred);
+    S.launches++;
+    return (np + 255) / 256;
+  }
+}
+
+// ------------------------------------------------------------------ factorisation: G = J J' = L L', XT = L^-T, Linv = L^-1
+static int factorize(lfpsqp_ctx *c, LargeState &S) {
+  const int m = S.m; const int64_t ldm = S.ldm;
+  cudaEventRecord(S.ev_g0, S.stream);
+  gemm_nt(S, m, m, (int)S.n_loc, S.J, S.ldj, S.J, S.ldj, S.G, ldm, GEMM_ASSIGN, 1);   // SYRK, lower tiles
+  cudaEventRecord(S.ev_g1, S.stream);
+  if (S.world > 1) comm_allreduce(S, S.G, (size_t)m * ldm);
+  diag_thresh_kernel<<<1, 256, 0, S.stream>>>(S.G, ldm, m, S.prm.eps_rank, S.thresh);
+  constexpr int NB = 64;
+  const size_t psm = 2 * NB * (NB + 1) * sizeof(double);
+  int nblk = (m + NB - 1) / NB;
+  for (int b = 0; b < nblk; b++) {
+    int j0 = b * NB, nb = std::min(NB, m - j0), rem = m - j0 - nb;
+    double *Ajj = S.G + (int64_t)j0 * ldm + j0, *Db = S.Dblk + (size_t)b * NB * NB;
+    potf2_inv_kernel<NB><<<1, 256, psm, S.stream>>>(Ajj, ldm, nb, Db, S.thresh, &S.ctrl->rankflag);
+    S.launches++;
+    if (rem > 0) {
+      double *A21 = S.G + (int64_t)(j0 + nb) * ldm + j0;
+      gemm_nt(S, rem, nb, nb, A21, ldm, Db, NB, A21, ldm, GEMM_ASSIGN, 0);                       // L21 = A21 D'
+      gemm_nt(S, rem, rem, nb, A21, ldm, A21, ldm, S.G + (int64_t)(j0 + nb) * ldm + (j0 + nb), ldm, GEMM_SUB, 1);  // A22 -= L21 L21'
+    }
+  }
+  // XT = L^-T (upper triangular, row-major), block row by block row; Linv = XT'
+  cudaMemsetAsync(S.XT, 0, (size_t)m * ldm * sizeof(double), S.stream);
+  for (int b = 0; b < nblk; b++) {
+    int i0 = b * NB, nb = std::min(NB, m - i0);
+    double *Db = S.Dblk + (size_t)b * NB * NB;
+    copy_block_T_kernel<<<(NB * NB + 255) / 256, 256, 0, S.stream>>>(Db, NB, nb, S.XT + (int64_t)i0 * ldm + i0, ldm);
+    S.launches++;
+    if (i0 > 0) {
+      gemm_nt(S, i0, nb, i0, S.XT, ldm, S.G + (int64_t)i0 * ldm, ldm, S.tmp64, NB, GEMM_ASSIGN, 0);   // P' = XT * L_i'
+      gemm_nt(S, i0, nb, nb, S.tmp64, NB, Db, NB, S.XT + i0, ldm, GEMM_ASSIGN_NEG, 0);              // XT[:, blk] = -P' D_i'
+    }
+  }
+  dim3 tg((m + 31) / 32, (m + 31) / 32);
+  transpose_kernel<<<tg, 256, 0, S.stream>>>(S.XT, ldm, S.Linv, ldm, m, m);
+  S.launches += 3;
+  S.factorizations++;
+  (void)c;
+  return 0;
+}
+
+// v <- v - J'(J J')^-1 J v ; with lam_out the multipliers u = (J J')^-1 J v  (optimize.jl:306-307, :333-343 ; App. B)
+// partial sums of the projected vector: slot0 = sum v^2, slot3 = max |v| (when want_norms)
+static void project(LargeState &S, double *v, double *lam_out, int pred, int want_norms) {
+  rows_dot(S, S.J, S.ldj, S.m, S.n_loc, v, S.tm, pred);
+  if (S.world > 1) comm_allreduce(S, S.tm, S.m);
+  gram_solve(S, S.tm, S.tu, lam_out, pred);
+  cols_dot(S, S.J, S.ldj, S.m, S.n_loc, S.tu, pred);
+  const double *cp = S.cpart; int ns = S.nsplit; int64_t n = S.n_loc;
+  vec(S, n, [=] __device__(int64_t j, double *acc) {
+    double s = 0.0;
+    for (int k = 0; k < ns; k++) s += cp[(int64_t)k * n + j];
+    double r = v[j] - s; v[j] = r;
+    acc[0] += r * r; acc[3] = fmax(acc[3], fabs(r));
+  }, 0, want_norms ? 1 : 0, want_norms);
+  S.launches++;
+}
+
+// ------------------------------------------------------------------ projcg! (projcg.jl:40-121), c = 0
+// b = S.d (projected -grad). Solution -> S.nd. Fills S.hctrl (status/iter/nr) on return.
+static int projcg(lfpsqp_ctx *c, LargeState &S, double tol, int64_t maxit, int chunk) {
+  const int64_t n = S.n_loc;
+  double *xs = S.nd, *r = S.w0, *dc = S.w1, *Ad = S.w2, *rp = S.w3, *gp = S.w4;
+  const double *b = S.d;
+  vec(S, n, [=] __device__(int64_t i, double *) { xs[i] = 0.0; r[i] = -b[i]; });
+  // g = r - U U' r (projcg.jl:59-60) ; r = g ; d = -g ; rg partials -> loop slot 3 (= 2 + (par^1) for k = 0)
+  rows_dot(S, S.J, S.ldj, S.m, n, r, S.tm, 0);
+  if (S.world > 1) comm_allreduce(S, S.tm, S.m);
+  gram_solve(S, S.tm, S.tu, nullptr, 0);
+  cols_dot(S, S.J, S.ldj, S.m, n, S.tu, 0);
+  cg_init_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, r, dc, S.cpart, S.nsplit, S.lp);
+  if (S.world > 1) comm_allreduce_loop_slot(S, 3, S.np_loop_raw);
+  S.launches += 2;
+  int64_t lim = std::min<int64_t>(maxit, S.n + S.m);   // min(maxit, n+m) with m = length(c) = rank (projcg.jl:71)
+  S.hctrl->tol = tol; S.hctrl->lim = (int)std::min<int64_t>(lim, 2000000000); S.hctrl->iter = 0; S.hctrl->status = (lim > 0) ? 0 : 4;
+  S.hctrl->nr = INFINITY;
+  write_ctrl_fields(S);
+  int64_t k = 0;
+  while (S.hctrl->status == 0) {
+    for (int q = 0; q < chunk; q++, k++) {
+      const int par = (int)(k & 1);
+      int nph = fam_hess(S, Ad, dc, S.x, S.lam, 1);
+      if (S.world > 1) comm_allreduce_loop_slot(S, 0, nph), nph = 1;
+      cg_update1_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, xs, dc, r, Ad, rp, S.lp, nph, S.np_loop, par, S.ctrl);
+      rows_dot(S, S.J, S.ldj, S.m, n, rp, S.tm, 1);
+      if (S.world > 1) comm_allreduce(S, S.tm, S.m);
+      gram_solve(S, S.tm, S.tu, nullptr, 1);
+      cols_dot(S, S.J, S.ldj, S.m, n, S.tu, 1);
+      cg_update2_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, rp, gp, S.cpart, S.nsplit, S.lp, par, S.ctrl, 1);
+      if (S.world > 1) comm_allreduce_loop_slots_cg(S, par);
+      cg_update3_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, dc, r, gp, S.lp, S.np_loop, par, S.ctrl);
+      S.launches += 3;
+    }
+    if (read_ctrl(c, S)) return -1;
+  }
+  S.projcg_iters += S.hctrl->iter;
+  if (S.hctrl->status == 2) {  // negative curvature: x = d/|d| (projcg.jl:77-82)
+    S.projcg_negcurv++;
+    vec(S, n, [=] __device__(int64_t i, double *acc) { acc[0] += dc[i] * dc[i]; }, 0, 1);
+    finalize(S, 1u, 0);
+    const LargeCtrl *ctrl = S.ctrl;
+    vec(S, n, [=] __device__(int64_t i, double *) { xs[i] = dc[i] / sqrt(ctrl->s[0]); });
+    S.launches += 2;
+    S.hctrl->nr = INFINITY;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ retract!(::ProjPenalty) (retractions.jl:265-441) + pcg! (:179-246)
+// xtil -> xnew ; returns flag, it1 (outer), it2 (pcg total)
+static int retract_pp(lfpsqp_ctx *c, LargeState &S, int *flag_out, int *it1, int *it2) {
+  const int64_t n = S.n_loc; const int m = S.m;
+  double *r = S.w0, *pv = S.w1, *z = S.w2, *dx = S.w3, *gv = S.w4, *xnew = S.xnew, *cval = S.cval;
+  const double *xtil = S.xtil;
+  const lfpsqp_params &prm = S.prm;
+  int flag = 0;
+  cudaMemcpyAsync(xnew, xtil, n * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);
+  double mu = prm.mu0;
+  int i = 0, pcg_total = 0;
+  while (i < prm.maxiter_retract) {
+    fam_c_jac(S, S.J, cval, xnew);                                                       // :340
+    // curtol = |c|_inf (slot 3 max), c.c (slot 0) ; g = xnew - xtilde, g.g (slot 1)
+    vec(S, m, [=] __device__(int64_t a, double *acc) { double v = cval[a]; acc[0] += v * v; acc[3] = fmax(acc[3], fabs(v)); }, 0, 1, 1);
+    finalize(S, 1u, 8u);
+    if (read_ctrl(c, S)) return -1;
+    double curtol = S.hctrl->s[3], cc = S.hctrl->s[0];
+    if (curtol < prm.eps_c) break;                                                       // :359-361
+    vec(S, n, [=] __device__(int64_t k, double *acc) { double t = xnew[k] - xtil[k]; gv[k] = t; acc[1] += t * t; }, 0, 2);
+    finalize(S, 2u, 0);
+    // g = J' c + mu g (:369) ; dx = 0 ; r = g ; r.r partials -> loop slot 5 (rho_0)
+    cols_dot(S, S.J, S.ldj, m, n, cval, 0);
+    {
+      const double *cp = S.cpart; int ns = S.nsplit; double *lp = S.lp; double muv = mu;
+      pp_rhs_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, gv, dx, r, pv, cp, ns, muv, lp);
+      S.launches++;
+    }
+    if (read_ctrl(c, S)) return -1;
+    double prev_obj = cc + mu * S.hctrl->s[1];                                           // :366
+    // pcg! with tol = eps_c, maxiter_pcg
+    S.hctrl->tol = prm.eps_c; S.hctrl->mu = mu; S.hctrl->pcg_iter = 0; S.hctrl->pcg_lim = (int)prm.maxiter_pcg; S.hctrl->pcg_status = 0;
+    write_ctrl_fields(S);
+    int64_t k = 0;
+    while (S.hctrl->pcg_status == 0) {
+      for (int q = 0; q < S.pcg_chunk; q++, k++) {
+        const int par = (int)(k & 1);
+        if (S.world > 1) comm_allreduce_loop_slot(S, 5 + par, S.np_loop_raw);
+        pcg_a_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, pv, r, S.lp, S.np_loop, par, k == 0, S.ctrl);
+        rows_dot(S, S.J, S.ldj, m, n, pv, S.tm, 2);
+        if (S.world > 1) comm_allreduce(S, S.tm, m);
+        cols_dot(S, S.J, S.ldj, m, n, S.tm, 2);
+        pcg_z_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, z, pv, S.cpart, S.nsplit, S.lp, S.ctrl);
+        if (S.world > 1) comm_allreduce_loop_slot(S, 4, S.np_loop_raw);
+        pcg_x_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, dx, r, pv, z, S.lp, S.np_loop, par, S.ctrl);
+        S.launches += 3;
+      }
+      if (read_ctrl(c, S)) return -1;
+    }
+    int pcg_i = S.hctrl->pcg_iter;
+    pcg_total += pcg_i;
+    if (pcg_i == prm.maxiter_pcg) { flag = 2; break; }                                   // :240-243, :377-381
+    // inner Armijo (:384-426)
+    vec(S, n, [=] __device__(int64_t q, double *acc) {
+      double xk = xnew[q]; pv[q] = xk;
+      acc[0] += gv[q] * dx[q];                     // ar_dot = -g.dx
+      xk -= dx[q]; xnew[q] = xk;
+      double t = xk - xtil[q]; gv[q] = t; acc[1] += t * t;
+    }, 0, 2);
+    fam_c_jac(S, nullptr, cval, xnew);                                                    // :392
+    vec(S, m, [=] __device__(int64_t a, double *acc) { double v = cval[a]; acc[0] += v * v; }, 2, 1);   // slot 2 only
+    S.launches += 2;
+    finalize(S, 7u, 0);
+    if (read_ctrl(c, S)) return -1;
+    double ar_dot = -S.hctrl->s[0], dist2 = S.hctrl->s[1], ccnew = S.hctrl->s[2];
+    double alpha = 1.0;
+    int armijo_count = 0;
+    while (ccnew + mu * dist2 > prev_obj + 1e-4 * alpha * ar_dot) {                      // :403
+      alpha /= 2;
+      double al = alpha;
+      vec(S, n, [=] __device__(int64_t q, double *acc) {
+        double xk = pv[q] - al * dx[q]; xnew[q] = xk;
+        double t = xk - xtil[q]; gv[q] = t; acc[0] += t * t;
+      }, 1, 1);                                                                           // slot 1 only
+      S.launches++;
+      finalize(S, 2u, 0);
+      if (read_ctrl(c, S)) return -1;
+      dist2 = S.hctrl->s[1];
+      // :410-417: the c-part of the merit stays frozen at its alpha = 1 value (stale cval quirk)
+      armijo_count++; S.pp_backtracks++;
+      if (armijo_count == 100) { flag = 3; break; }
+    }
+    i++;
+    mu = std::min(mu * 0.1, sqrt(ccnew));                                                // :431 (norm of the stale cvalaug)
+  }
+  if (i == prm.maxiter_retract) flag = 1;
+  *flag_out = flag; *it1 = i; *it2 = pcg_total;
+  return 0;
+}
+
+// ------------------------------------------------------------------ retract!(::NR) (retractions.jl:75-177), Cholesky-QR basis (App. B)
+static int retract_nr(lfpsqp_ctx *c, LargeState &S, int *flag_out, int *it1) {
+  const int64_t n = S.n_loc; const int m = S.m; const int64_t ldm = S.ldm;
+  double *xnew = S.xnew, *cval = S.cval, *D = S.Dnr, *t1 = S.nr_t1, *t2 = S.nr_t2, *dcv = S.nr_dc;
+  cudaMemcpyAsync(xnew, S.xtil, n * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);
+  fam_c_jac(S, nullptr, cval, xnew);
+  cudaMemcpyAsync(D, S.Linv, (size_t)m * ldm * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);   // D0 = L^-1
+  int i = 0;
+  while (i < S.prm.maxiter_retract) {
+    vec(S, m, [=] __device__(int64_t a, double *acc) { acc[3] = fmax(acc[3], fabs(cval[a])); }, 0, 0, 1);
+    finalize(S, 0, 8u);
+    if (read_ctrl(c, S)) return -1;
+    if (S.hctrl->s[3] < S.prm.eps_c) break;                                              // :135
+    rows_dot(S, D, ldm, m, m, cval, t1, 0);                                              // D c
+    vec(S, m, [=] __device__(int64_t a, double *) { t1[a] = -t1[a]; });                   // :140 delta = -D c
+    // xnew += Q delta, Q = J' L^-T (:141)
+    tri_gemv_kernel<<<(m + 7) / 8, 256, m * sizeof(double), S.stream>>>(S.XT, ldm, m, t1, S.tu, 1, nullptr, S.ctrl, 0);
+    cols_dot(S, S.J, S.ldj, m, n, S.tu, 0);
+    { const double *cp = S.cpart; int ns = S.nsplit;
+      vec(S, n, [=] __device__(int64_t j, double *) { double s = 0.0; for (int k = 0; k < ns; k++) s += cp[(int64_t)k * n + j]; xnew[j] += s; }); }
+    fam_c_jac(S, nullptr, t2, xnew);                                                     // :144-149
+    vec(S, m, [=] __device__(int64_t a, double *) { dcv[a] = t2[a] - cval[a]; cval[a] = t2[a]; });
+    // Good Broyden (:156-160): t2 = D' delta ; t1 = delta - D dc ; D += t1 t2' / (t2.dc)
+    {
+      dim3 grid((unsigned)((m + 511) / 512), S.nsplit);
+      cols_dot_kernel<<<grid, 256, S.rows_per_split * sizeof(double), S.stream>>>(D, ldm, m, m, t1, S.cpart, S.rows_per_split, S.ctrl, 0);
+      const double *cp = S.cpart; int ns = S.nsplit;
+      vec(S, m, [=] __device__(int64_t a, double *acc) {
+        double s = 0.0; for (int k = 0; k < ns; k++) s += cp[(int64_t)k * m + a];
+        t2[a] = s; acc[0] += s * dcv[a];
+      }, 0, 1);
+      finalize(S, 1u, 0);
+      rows_dot(S, D, ldm, m, m, dcv, S.tm, 0);
+      double *tmv = S.tm;
+      vec(S, m, [=] __device__(int64_t a, double *) { t1[a] -= tmv[a]; });
+      const LargeCtrl *ctrl = S.ctrl;
+      vec(S, (int64_t)m * m, [=] __device__(int64_t e, double *) {
+        int rr = (int)(e / m), cc2 = (int)(e % m);
+        D[(int64_t)rr * ldm + cc2] += (1.0 / ctrl->s[0]) * t1[rr] * t2[cc2];
+      });
+    }
+    S.launches += 9;
+    i++;
+  }
+  *flag_out = (i == S.prm.maxiter_retract) ? 1 : 0; *it1 = i;
+  return 0;
+}
+
+// ------------------------------------------------------------------ the driver (optimize.jl:119-443, no bounds)
+static int solve(lfpsqp_ctx *c, LargeState &S, const double *x0_host, double *x_out, double *obj_hist, int64_t H,
+                 int64_t *obj_len, double *lambda, lfpsqp_term *term, lfpsqp_stats *stats) {
+  const int64_t n = S.n_loc; const int m = S.m;
+  const lfpsqp_params &prm = S.prm;
+  double *x = S.x, *g = S.g, *d = S.d, *xnew = S.xnew, *xtil = S.xtil, *nd = S.nd;
+  S.reset_counters();
+  CK(cudaMemcpyAsync(x, x0_host, n * sizeof(double), cudaMemcpyHostToDevice, S.stream));
+  memset(S.hctrl, 0, sizeof(LargeCtrl));
+  write_ctrl_fields(S);
+  int64_t it = 0, nobj = 0;
+  double f_diff = INFINITY, step_diff = INFINITY, kkt_diff = INFINITY, prev_grad_norm = 0.0;
+  fam_f(S, x); finalize(S, 1u, 0);
+  if (m > 0) fam_c_jac(S, nullptr, S.cval, x);                                          // :252
+  if (read_ctrl(c, S)) return LFPSQP_ERR_CUDA;
+  double fval = S.hctrl->s[0];
+  if (nobj < H) obj_hist[nobj] = fval;
+  nobj++;
+  int cond = LFPSQP_F_TOL, status = 0, last_flag = 0;
+  while (true) {
+    fam_grad(S, g, x);                                                                  // :259
+    vec(S, n, [=] __device__(int64_t i, double *) { d[i] = -1.0 * g[i]; });              // :262
+    S.launches++;
+    if (m > 0) {
+      fam_c_jac(S, S.J, S.cval, x);                                                     // :283
+      if (factorize(c, S)) return LFPSQP_ERR_CUDA;
+      project(S, d, S.lam, 0, 1);                                                       // :306-307, :333-343
+    } else {
+      vec(S, n, [=] __device__(int64_t i, double *acc) { double r = d[i]; acc[0] += r * r; acc[3] = fmax(acc[3], fabs(r)); }, 0, 1, 1);
+    }
+    finalize(S, 1u, 8u);
+    if (read_ctrl(c, S)) return LFPSQP_ERR_CUDA;
+    if (S.hctrl->rankflag) { status |= LFPSQP_ST_RANK_DEFICIENT; cond = LFPSQP_MAX_ITER; break; }
+    kkt_diff = S.hctrl->s[3];                                                           // :320
+    double gn = sqrt(S.hctrl->s[0]);
+    if (f_diff <= prm.eps_f) { cond = LFPSQP_F_TOL; break; }                            // :347-359
+    else if (step_diff <= prm.eps_x) { cond = LFPSQP_X_TOL; break; }
+    else if (it >= prm.maxiter) { cond = LFPSQP_MAX_ITER; break; }
+    else if (kkt_diff <= prm.eps_kkt) { cond = LFPSQP_KKT_TOL; break; }
+    if (!(kkt_diff == kkt_diff)) { status |= LFPSQP_ST_NONFINITE; cond = LFPSQP_MAX_ITER; break; }
+    if (prm.do_newton) {                                                                // :364-390
+      double tol = prm.tn_kappa * fmin(1.0, gn / prev_grad_norm) * gn;
+      prev_grad_norm = gn;
+      fam_hess_prepare(S, x, S.lam);
+      if (projcg(c, S, tol, prm.tn_maxiter, S.cg_chunk)) return LFPSQP_ERR_CUDA;
+      vec(S, n, [=] __device__(int64_t i, double *acc) { acc[0] += nd[i] * d[i]; }, 0, 1);
+      finalize(S, 1u, 0);
+      if (read_ctrl(c, S)) return LFPSQP_ERR_CUDA;
+      if (S.hctrl->s[0] > 0.0) { cudaMemcpyAsync(d, nd, n * sizeof(double), cudaMemcpyDeviceToDevice, S.stream); S.newton_accepted++; }
+    }
+    const int kind = (m > 0) ? ((!prm.do_project_retract) ? 2 : 3) : 0;                 // :396-412 (rank == m here)
+    // armijo! (linesearch.jl:32-89)
+    vec(S, n, [=] __device__(int64_t i, double *acc) { acc[0] += d[i] * g[i]; }, 0, 1);
+    finalize(S, 1u, 0);
+    if (read_ctrl(c, S)) return LFPSQP_ERR_CUDA;
+    const double ar_dot = S.hctrl->s[0];
+    double alpha = prm.alpha, newf = 0.0;
+    f_diff = INFINITY; step_diff = INFINITY;
+    int flag = 0;
+    while (step_diff > prm.eps_x) {
+      double al = alpha;
+      vec(S, n, [=] __device__(int64_t i, double *) { xtil[i] = x[i] + al * d[i]; });
+      int i1 = 0, i2 = 0;
+      if (kind == 0) cudaMemcpyAsync(xnew, xtil, n * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);
+      else if (kind == 2) { if (retract_nr(c, S, &flag, &i1)) return LFPSQP_ERR_CUDA; }
+      else { if (retract_pp(c, S, &flag, &i1, &i2)) return LFPSQP_ERR_CUDA; }
+      S.retract_outer += i1; S.retract_pcg += i2; S.armijo_trials++;
+      if (flag > 0) { alpha *= prm.s; continue; }                                       // :57-60
+      fam_f(S, xnew);
+      vec(S, n, [=] __device__(int64_t i, double *acc) { double t = xnew[i] - x[i]; acc[0] += t * t; }, 1, 1);   // slot 1 only
+      finalize(S, 3u, 0);
+      if (read_ctrl(c, S)) return LFPSQP_ERR_CUDA;
+      newf = S.hctrl->s[0];
+      step_diff = sqrt(S.hctrl->s[1]);
+      f_diff = fabs(newf - fval);
+      if (prm.disable_linesearch) break;
+      if ((newf - fval) <= prm.sigma * alpha * ar_dot) break;                           // :75
+      alpha *= prm.s;
+      if (alpha < 1e-100) { flag = 99; break; }
+    }
+    last_flag = flag;
+    cudaMemcpyAsync(x, xnew, n * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);    // :424
+    fval = newf;
+    if (nobj < H) obj_hist[nobj] = fval;
+    nobj++;
+    it++;
+  }
+  CK(cudaMemcpyAsync(x_out, x, n * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+  if (m > 0) CK(cudaMemcpyAsync(lambda, S.lam, m * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+  CK(cudaStreamSynchronize(S.stream));
+  *obj_len = nobj;
+  term->condition = cond; term->status = status; term->f_diff = f_diff; term->step_diff = step_diff;
+  term->kkt_diff = kkt_diff; term->iter = it;
+  if (stats) {
+    stats->projcg_iters = S.projcg_iters; stats->projcg_negcurv = S.projcg_negcurv; stats->armijo_trials = S.armijo_trials;
+    stats->retract_outer = S.retract_outer; stats->retract_pcg = S.retract_pcg; stats->pp_backtracks = S.pp_backtracks;
+    stats->newton_accepted = S.newton_accepted; stats->factorizations = S.factorizations; stats->f_evals = S.f_evals;
+    stats->flag_last = last_flag;
+  }
+  c->last_launches = S.launches;
+  return LFPSQP_OK;
+}
+
+// ------------------------------------------------------------------ setup / teardown
+void lfpsqp_large_release(lfpsqp_ctx *c) {
+  if (!c->large) return;
+  LargeState *S = c->large;
+  cudaSetDevice(c->device);
+  for (void *p : S->owned) cudaFree(p);
+  if (S->hctrl) cudaFreeHost(S->hctrl);
+  if (S->ev_g0) cudaEventDestroy(S->ev_g0);
+  if (S->ev_g1) cudaEventDestroy(S->ev_g1);
+  comm_release(*S);
+  delete S;
+  c->large = nullptr;
+}
+
+template <class T> static bool dalloc(LargeState &S, T **p, size_t count) {
+  void *q = nullptr;
+  if (cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return false; }
+  S.owned.push_back(q); *p = (T *)q;
+  return true;
+}
+
+extern "C" int lfpsqp_large_setup(lfpsqp_ctx *c, int family, int64_t n_global, int64_t m, int64_t col0, int64_t n_loc,
+                                  const double *params, int params_on_device) {
+  if (!c) return LFPSQP_ERR_ARG;
+  cudaSetDevice(c->device);
+  if (family != LFPSQP_FAM_DIAGQUAD && family != LFPSQP_FAM_THOMSON)
+    return c->fail(LFPSQP_ERR_FAMILY, "large-n mode supports the DIAGQUAD and THOMSON families");
+  if (n_global < 1 || m < 0 || n_loc < 1 || col0 < 0 || col0 + n_loc > n_global || m > n_global)
+    return c->fail(LFPSQP_ERR_ARG, "bad sizes for large-n setup");
+  if (family == LFPSQP_FAM_THOMSON && (n_global % 3 || m != n_global / 3 || n_loc != n_global))
+    return c->fail(LFPSQP_ERR_FAMILY, "THOMSON needs n = 3 m and runs on one GPU (its callbacks need all of x)");
+  if (m > 16384) return c->fail(LFPSQP_ERR_ARG, "m too large for the replicated factor");
+  // keep the communicator across setups
+  LargeState *old = c->large; CommState comm;
+  if (old) { comm = old->comm; old->comm = CommState(); }
+  lfpsqp_large_release(c);
+  LargeState *Sp = new LargeState(); LargeState &S = *Sp;
+  c->large = Sp;
+  S.comm = comm; S.world = comm.world > 0 ? comm.world : 1; S.rank = comm.rank;
+  if (S.world > 1 && family == LFPSQP_FAM_THOMSON) return c->fail(LFPSQP_ERR_FAMILY, "THOMSON is single-GPU");
+  S.family = family; S.n = n_global; S.n_loc = n_loc; S.col0 = col0; S.m = (int)m; S.stream = c->stream;
+  S.sm_count = c->sm_count; S.ldj = up2(n_loc); S.ldm = up2(std::max<int64_t>(m, 1));
+  S.vgrid = (int)std::min<int64_t>(std::max<int64_t>((n_loc + 255) / 256, 1), std::min<int64_t>(MAXP, 4 * (int64_t)c->sm_count));
+  S.np_loop_raw = S.vgrid; S.np_loop = (S.world > 1) ? 1 : S.vgrid;
+  // row splits of pass 2: enough CTAs to fill the GPU, at least 32 rows per split
+  {
+    int64_t coltiles = (n_loc + 511) / 512;
+    int want = (int)std::max<int64_t>(1, (4LL * c->sm_count + coltiles - 1) / coltiles);
+    int maxs = std::max(1, (int)m / 32);
+    S.nsplit = std::max(1, std::min(std::min(want, maxs), 64));
+    S.rows_per_split = m > 0 ? (int)((m + S.nsplit - 1) / S.nsplit) : 1;
+    S.nsplit = m > 0 ? (int)((m + S.rows_per_split - 1) / S.rows_per_split) : 1;
+  }
+  S.cg_chunk = 2; S.pcg_chunk = 2;
+  const size_t nl = (size_t)n_loc, mm = (size_t)std::max<int64_t>(m, 1);
+  bool ok = true;
+  ok &= dalloc(S, &S.J, mm * S.ldj);
+  ok &= dalloc(S, &S.G, mm * S.ldm); ok &= dalloc(S, &S.XT, mm * S.ldm); ok &= dalloc(S, &S.Linv, mm * S.ldm);
+  ok &= dalloc(S, &S.Dblk, ((mm + 63) / 64) * 64 * 64); ok &= dalloc(S, &S.tmp64, mm * 64); ok &= dalloc(S, &S.thresh, 8);
+  S.gemm_ws_bytes = std::max<size_t>((size_t)16 * mm * 64 * 8, std::min<size_t>(mm * mm * 8 * 8, (size_t)256 << 20));
+  { char *ws = nullptr; ok &= dalloc(S, &ws, S.gemm_ws_bytes); S.gemm_ws = (double *)ws; }
+  double **vecs[] = {&S.x, &S.xnew, &S.xtil, &S.g, &S.d, &S.nd, &S.w0, &S.w1, &S.w2, &S.w3, &S.w4, &S.hdiag};
+  for (double **v : vecs) ok &= dalloc(S, v, nl + 2);
+  double **mv[] = {&S.cval, &S.lam, &S.tm, &S.ty, &S.tu, &S.nr_t1, &S.nr_t2, &S.nr_dc};
+  for (double **v : mv) ok &= dalloc(S, v, mm + 2);
+  ok &= dalloc(S, &S.cpart, (size_t)S.nsplit * std::max(nl, mm) + 2);
+  ok &= dalloc(S, &S.lp, (size_t)NSLOT * MAXP); ok &= dalloc(S, &S.gpart, (size_t)NSLOT * MAXP);
+  ok &= dalloc(S, &S.ctrl, 1); ok &= dalloc(S, &S.commbuf, 64);
+  S.Dnr = nullptr;
+  if (!ok) { lfpsqp_large_release(c); return c->fail(LFPSQP_ERR_NOMEM, "large-n setup: device allocation failed"); }
+  if (cudaMallocHost((void **)&S.hctrl, sizeof(LargeCtrl)) != cudaSuccess) { lfpsqp_large_release(c); return c->fail(LFPSQP_ERR_NOMEM, "pinned allocation failed"); }
+  cudaEventCreate(&S.ev_g0); cudaEventCreate(&S.ev_g1);
+  cudaMemsetAsync(S.lp, 0, (size_t)NSLOT * MAXP * 8, S.stream); cudaMemsetAsync(S.gpart, 0, (size_t)NSLOT * MAXP * 8, S.stream);
+  cudaMemsetAsync(S.ctrl, 0, sizeof(LargeCtrl), S.stream);
+  // parameters
+  if (family == LFPSQP_FAM_DIAGQUAD) {
+    const size_t cnt = 2 * mm * nl * (m > 0 ? 1 : 0) + (size_t)m + 2 * nl;
+    if (!params) { lfpsqp_large_release(c); return c->fail(LFPSQP_ERR_ARG, "DIAGQUAD needs a parameter blob"); }
+    if (S.ldj != n_loc) { lfpsqp_large_release(c); return c->fail(LFPSQP_ERR_ARG, "large-n mode needs an even local column count"); }
+    const double *blob = params;
+    if (!params_on_device) {
+      double *dev = nullptr;
+      if (!dalloc(S, &dev, cnt)) { lfpsqp_large_release(c); return c->fail(LFPSQP_ERR_NOMEM, "parameter allocation failed"); }
+      CK(cudaMemcpyAsync(dev, params, cnt * 8, cudaMemcpyHostToDevice, S.stream));
+      blob = dev;
+    }
+    S.p_Q = blob; S.p_A = blob + (size_t)m * nl; S.p_b = S.p_A + (size_t)m * nl; S.p_xt = S.p_b + m; S.p_w = S.p_xt + nl;
+    if ((((uintptr_t)S.p_A) & 15) || (((uintptr_t)S.p_Q) & 15)) { lfpsqp_large_release(c); return c->fail(LFPSQP_ERR_ARG, "parameter blob must be 16-byte aligned"); }
+  }
+  cudaFuncSetAttribute(dgemm_nt_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgemm_smem_bytes<128>());
+  cudaFuncSetAttribute(dgemm_nt_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgemm_smem_bytes<64>());
+  cudaFuncSetAttribute(potf2_inv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 64 * 65 * sizeof(double)));
+  CK(cudaStreamSynchronize(S.stream));
+  return LFPSQP_OK;
+}
+
+static int need_large(lfpsqp_ctx *c) {
+  if (!c) return LFPSQP_ERR_ARG;
+  if (!c->large) return c->fail(LFPSQP_ERR_ARG, "call lfpsqp_large_setup first");
+  cudaSetDevice(c->device);
+  c->large->stream = c->stream;
+  return 0;
+}
+static int prep_params(lfpsqp_ctx *c, LargeState &S, const lfpsqp_params *prm) {
+  if (!prm) return c->fail(LFPSQP_ERR_ARG, "params is NULL");
+  if (prm->beta > 0) return c->fail(LFPSQP_ERR_UNSUPPORTED, "beta>0 is not supported on the device path");
+  if (prm->linesearch != 0 && !prm->disable_linesearch) return c->fail(LFPSQP_ERR_UNSUPPORTED, "linesearch=exact is not on the device path yet");
+  S.prm = *prm;
+  if (!prm->do_project_retract && S.m > 0 && !S.Dnr) {
+    if (!dalloc(S, &S.Dnr, (size_t)S.m * S.ldm)) return c->fail(LFPSQP_ERR_NOMEM, "NR workspace allocation failed");
+  }
+  return 0;
+}
+
+extern "C" int lfpsqp_large_solve(lfpsqp_ctx *c, const double *x0_loc, const lfpsqp_params *prm, double *x_out_loc,
+                                  double *obj_hist, int64_t H, int64_t *obj_len, double *lambda, lfpsqp_term *term,
+                                  lfpsqp_stats *stats) {
+  int rc = need_large(c); if (rc) return rc;
+  LargeState &S = *c->large;
+  rc = prep_params(c, S, prm); if (rc) return rc;
+  if (H < 1) return c->fail(LFPSQP_ERR_ARG, "H must be >= 1");
+  cudaEventRecord(c->ev0, S.stream);
+  rc = solve(c, S, x0_loc, x_out_loc, obj_hist, H, obj_len, lambda, term, stats);
+  if (rc) return rc;
+  cudaEventRecord(c->ev1, S.stream);
+  cudaEventSynchronize(c->ev1);
+  float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->last_ms = ms;
+  return LFPSQP_OK;
+}
+
+// optimize(...) for one large instance on one GPU with host-resident family parameters
+extern "C" int lfpsqp_solve_large(lfpsqp_ctx *c, int family, int64_t n, int64_t m, const double *fam_params,
+                                  const double *x0, const double *xl, const double *xu, const lfpsqp_params *prm,
+                                  double *x_out, double *obj_hist, int64_t H, int64_t *obj_len, double *lambda,
+                                  lfpsqp_term *term, lfpsqp_stats *stats) {
+  if (!c) return LFPSQP_ERR_ARG;
+  if (xl || xu) {
+    if (!xl || !xu) return c->fail(LFPSQP_ERR_ARG, "xl and xu must both be given or both be NULL");
+    for (int64_t i = 0; i < n; i++) {
+      if (xl[i] > xu[i]) return c->fail(LFPSQP_ERR_BOUNDS, "Infeasible: lower bounds cannot be greater than upper bounds");
+      if (!(xl[i] == -INFINITY && xu[i] == INFINITY))
+        return c->fail(LFPSQP_ERR_UNSUPPORTED, "finite bounds are not supported in large-n mode yet (use batched mode)");
+    }
+  }
+  int rc = lfpsqp_large_setup(c, family, n, m, 0, n, fam_params, 0);
+  if (rc) return rc;
+  return lfpsqp_large_solve(c, x0, prm, x_out, obj_hist, H, obj_len, lambda, term, stats);
+}
+
+// Unit-level: factorisation of the Jacobian at x (ksvd! replacement) -- G = J J' (lower), L, L^-1 returned to the host
+extern "C" int lfpsqp_large_factor(lfpsqp_ctx *c, const double *x_loc, double *G_out, double *L_out, double *Linv_out,
+                                   int *rank_deficient, double *gram_ms) {
+  int rc = need_large(c); if (rc) return rc;
+  LargeState &S = *c->large;
+  lfpsqp_params p; lfpsqp_default_params(&p); S.prm = p;
+  const int m = S.m; const size_t ldm = S.ldm;
+  CK(cudaMemcpyAsync(S.x, x_loc, S.n_loc * 8, cudaMemcpyHostToDevice, S.stream));
+  memset(S.hctrl, 0, sizeof(LargeCtrl)); write_ctrl_fields(S);
+  fam_c_jac(S, S.J, S.cval, S.x);
+  if (G_out) {  // G before it is overwritten by L
+    gemm_nt(S, m, m, (int)S.n_loc, S.J, S.ldj, S.J, S.ldj, S.G, ldm, GEMM_ASSIGN, 1);
+    if (S.world > 1) comm_allreduce(S, S.G, (size_t)m * ldm);
+    CK(cudaMemcpy2DAsync(G_out, m * 8, S.G, ldm * 8, m * 8, m, cudaMemcpyDeviceToHost, S.stream));
+  }
+  factorize(c, S);
+  if (read_ctrl(c, S)) return LFPSQP_ERR_CUDA;
+  if (L_out) CK(cudaMemcpy2DAsync(L_out, m * 8, S.G, ldm * 8, m * 8, m, cudaMemcpyDeviceToHost, S.stream));
+  if (Linv_out) CK(cudaMemcpy2DAsync(Linv_out, m * 8, S.Linv, ldm * 8, m * 8, m, cudaMemcpyDeviceToHost, S.stream));
+  CK(cudaStreamSynchronize(S.stream));
+  if (rank_deficient) *rank_deficient = S.hctrl->rankflag;
+  if (gram_ms) { float ms = 0; cudaEventElapsedTime(&ms, S.ev_g0, S.ev_g1); *gram_ms = ms; }
+  return LFPSQP_OK;
+}
+
+// Unit-level: tangent projection v - J'(J J')^-1 J v with the factor cached by lfpsqp_large_factor (kgemv! pair,
+// optimize.jl:306-307) and the multipliers (J J')^-1 J v (optimize.jl:333-343)
+extern "C" int lfpsqp_large_project(lfpsqp_ctx *c, const double *v_loc, double *v_out_loc, double *lambda_out) {
+  int rc = need_large(c); if (rc) return rc;
+  LargeState &S = *c->large;
+  CK(cudaMemcpyAsync(S.d, v_loc, S.n_loc * 8, cudaMemcpyHostToDevice, S.stream));
+  project(S, S.d, S.lam, 0, 0);
+  CK(cudaMemcpyAsync(v_out_loc, S.d, S.n_loc * 8, cudaMemcpyDeviceToHost, S.stream));
+  if (lambda_out && S.m > 0) CK(cudaMemcpyAsync(lambda_out, S.lam, S.m * 8, cudaMemcpyDeviceToHost, S.stream));
+  CK(cudaStreamSynchronize(S.stream));
+  return LFPSQP_OK;
+}
+
+// Unit-level + benchmark: projcg! (projcg.jl:40-121) at the point x with multipliers lam, right-hand side b = P(-grad f(x)),
+// tolerance tol, at most maxit iterations (tol = 0 with maxit = K times a fixed number of iterations: the
+// "projcg iterations / s" metric).  Needs lfpsqp_large_factor at the same x first.  ms = device time of the loop.
+extern "C" int lfpsqp_large_projcg(lfpsqp_ctx *c, const double *x_loc, const double *lam, double tol, int64_t maxit,
+                                   int chunk, double *sol_out_loc, int64_t *iters, double *nr, int *status, double *ms) {
+  int rc = need_large(c); if (rc) return rc;
+  LargeState &S = *c->large;
+  const int64_t n = S.n_loc;
+  double *g = S.g, *d = S.d;
+  CK(cudaMemcpyAsync(S.x, x_loc, n * 8, cudaMemcpyHostToDevice, S.stream));
+  if (S.m > 0) { if (lam) CK(cudaMemcpyAsync(S.lam, lam, S.m * 8, cudaMemcpyHostToDevice, S.stream)); else cudaMemsetAsync(S.lam, 0, S.m * 8, S.stream); }
+  memset(S.hctrl, 0, sizeof(LargeCtrl)); write_ctrl_fields(S);
+  fam_grad(S, g, S.x);
+  vec(S, n, [=] __device__(int64_t i, double *) { d[i] = -1.0 * g[i]; });
+  if (S.m > 0) project(S, d, nullptr, 0, 0);
+  fam_hess_prepare(S, S.x, S.lam);
+  S.reset_counters();
+  cudaEventRecord(c->ev0, S.stream);
+  if (projcg(c, S, tol, maxit, chunk > 0 ? chunk : S.cg_chunk)) return LFPSQP_ERR_CUDA;
+  cudaEventRecord(c->ev1, S.stream);
+  if (sol_out_loc) CK(cudaMemcpyAsync(sol_out_loc, S.nd, n * 8, cudaMemcpyDeviceToHost, S.stream));
+  CK(cudaStreamSynchronize(S.stream));
+  float t = 0; cudaEventElapsedTime(&t, c->ev0, c->ev1);
+  if (ms) *ms = t;
+  if (iters) *iters = S.hctrl->iter;
+  if (nr) *nr = S.hctrl->nr;
+  if (status) *status = S.hctrl->status;
+  c->last_ms = t; c->last_launches = S.launches;
+  return LFPSQP_OK;
+}

@@ -1,0 +1,128 @@
+// large_families.cuh -- device callbacks of the benchmark families for the large-n mode (whole-GPU kernels).
+// Same contract as the batched callbacks (src/autodiff_generators.jl:7-9, :40-42, :80-104), but every call is a
+// grid-wide kernel over the column shard [col0, col0+n_loc) this GPU owns.
+#pragma once
+#include "large_kernels.cuh"
+
+namespace lfpsqp {
+
+// ================================================================== DIAGQUAD (BASELINE config C5)
+// c_i = 1/2 sum_j Q_ij x_j^2 + A_i.x - b_i ; f = 1/2 sum_j w_j (x_j - xt_j)^2 ; Q, A: m x n_loc row-major shards.
+
+// raw row sums s_i = sum_j (1/2 Q_ij x_j + A_ij) x_j  (b is subtracted after the cross-GPU reduction);
+// WRITE_J also stores J_ij = Q_ij x_j + A_ij (jac!, which "also writes cval": autodiff_generators.jl:40-42)
+template <int R, bool WRITE_J>
+__global__ void __launch_bounds__(256) dq_rows_kernel(const double *__restrict__ Q, const double *__restrict__ A, int64_t ld,
+                                                      int m, int64_t ncols, const double *__restrict__ x,
+                                                      double *__restrict__ J, double *__restrict__ rows) {
+  __shared__ double sh[33];
+  const int row0 = blockIdx.x * R;
+  double acc[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) acc[r] = 0.0;
+  const int64_t n2 = ncols >> 1;
+  for (int64_t j = threadIdx.x; j < n2; j += 256 * 2) {
+    double2 xv[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      int64_t jj = j + (int64_t)u * 256;
+      xv[u] = (jj < n2) ? *reinterpret_cast<const double2 *>(x + 2 * jj) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      if (row0 + r >= m) continue;
+      const int64_t off = (int64_t)(row0 + r) * ld;
+      double2 q[2], a[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        int64_t jj = j + (int64_t)u * 256;
+        q[u] = (jj < n2) ? ld_stream2(Q + off + 2 * jj) : make_double2(0.0, 0.0);
+        a[u] = (jj < n2) ? ld_stream2(A + off + 2 * jj) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        int64_t jj = j + (int64_t)u * 256;
+        acc[r] += (0.5 * q[u].x * xv[u].x + a[u].x) * xv[u].x + (0.5 * q[u].y * xv[u].y + a[u].y) * xv[u].y;
+        if (WRITE_J && jj < n2)
+          *reinterpret_cast<double2 *>(J + off + 2 * jj) = make_double2(q[u].x * xv[u].x + a[u].x, q[u].y * xv[u].y + a[u].y);
+      }
+    }
+  }
+  if ((ncols & 1) && threadIdx.x == 0) {
+    int64_t jl = ncols - 1;
+#pragma unroll
+    for (int r = 0; r < R; r++) if (row0 + r < m) {
+      int64_t off = (int64_t)(row0 + r) * ld + jl;
+      acc[r] += (0.5 * Q[off] * x[jl] + A[off]) * x[jl];
+      if (WRITE_J) J[off] = Q[off] * x[jl] + A[off];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    double s = block_sum(acc[r], sh);
+    if (threadIdx.x == 0 && row0 + r < m) rows[row0 + r] = s;
+  }
+}
+
+// ================================================================== THOMSON (BASELINE config C4), single-GPU shard
+// One thread per point i, all points j streamed through shared memory in tiles of 256.
+// mode 0: f partials (sum_{j!=i} 1/r_ij, halved)      -> part slot s0
+// mode 1: gradient g_i = -sum_j (x_i-x_j)/r^3
+// mode 2: Hessian action dest_i = sum_j [3 r (r.w)/r^5 - w/r^3] + 2 lam_i v_i  (w = v_i - v_j) and partial v.dest -> slot s0
+template <int MODE>
+__global__ void __launch_bounds__(256) thomson_pair_kernel(int np_, const double *__restrict__ x, const double *__restrict__ v,
+                                                           const double *__restrict__ lam, double *__restrict__ out,
+                                                           double *part, int s0, const LargeCtrl *ctrl, int pred) {
+  if (pred == 1 && ctrl->status != 0) return;
+  __shared__ double xs[256 * 3];
+  __shared__ double vs[MODE == 2 ? 256 * 3 : 3];
+  __shared__ double sh[33];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const bool act = i < np_;
+  double xi = 0, yi = 0, zi = 0, vx = 0, vy = 0, vz = 0;
+  if (act) { xi = x[3 * i]; yi = x[3 * i + 1]; zi = x[3 * i + 2]; if (MODE == 2) { vx = v[3 * i]; vy = v[3 * i + 1]; vz = v[3 * i + 2]; } }
+  double a0 = 0, a1 = 0, a2 = 0;
+  for (int j0 = 0; j0 < np_; j0 += 256) {
+    __syncthreads();
+    int jn = min(256, np_ - j0);
+    for (int e = threadIdx.x; e < jn * 3; e += 256) { xs[e] = x[3 * j0 + e]; if (MODE == 2) vs[e] = v[3 * j0 + e]; }
+    __syncthreads();
+    if (act) {
+      for (int jj = 0; jj < jn; jj++) {
+        if (j0 + jj == i) continue;
+        double a = xi - xs[3 * jj], b = yi - xs[3 * jj + 1], c = zi - xs[3 * jj + 2];
+        double r2 = a * a + b * b + c * c;
+        if (MODE == 0) { a0 += 1.0 / sqrt(r2); }
+        else if (MODE == 1) { double ir3 = 1.0 / (r2 * sqrt(r2)); a0 -= a * ir3; a1 -= b * ir3; a2 -= c * ir3; }
+        else {
+          double wa = vx - vs[3 * jj], wb = vy - vs[3 * jj + 1], wc = vz - vs[3 * jj + 2];
+          double ir3 = 1.0 / (r2 * sqrt(r2)), ir5 = ir3 / r2, rw = 3.0 * (a * wa + b * wb + c * wc) * ir5;
+          a0 += rw * a - wa * ir3; a1 += rw * b - wb * ir3; a2 += rw * c - wc * ir3;
+        }
+      }
+    }
+  }
+  double pr = 0.0;
+  if (MODE == 0) pr = act ? 0.5 * a0 : 0.0;
+  else if (MODE == 1) { if (act) { out[3 * i] = a0; out[3 * i + 1] = a1; out[3 * i + 2] = a2; } }
+  else if (act) {
+    double l2 = 2.0 * lam[i];
+    a0 += l2 * vx; a1 += l2 * vy; a2 += l2 * vz;
+    out[3 * i] = a0; out[3 * i + 1] = a1; out[3 * i + 2] = a2;
+    pr = vx * a0 + vy * a1 + vz * a2;
+  }
+  if (MODE != 1) {
+    pr = block_sum(pr, sh);
+    if (threadIdx.x == 0) part[(size_t)s0 * MAXP + blockIdx.x] = pr;
+  }
+}
+// c_i = |x_i|^2 - 1 ; optionally the three structural non-zeros of row i of the (dense-treated) Jacobian
+__global__ void thomson_c_kernel(int np_, const double *__restrict__ x, double *__restrict__ cval, double *J, int64_t ld) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= np_) return;
+  double a = x[3 * i], b = x[3 * i + 1], c = x[3 * i + 2];
+  cval[i] = a * a + b * b + c * c - 1.0;
+  if (J) { double *r = J + (int64_t)i * ld + 3 * i; r[0] = 2.0 * a; r[1] = 2.0 * b; r[2] = 2.0 * c; }
+}
+
+}  // namespace lfpsqp

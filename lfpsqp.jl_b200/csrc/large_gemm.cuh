@@ -1,0 +1,234 @@
+// large_gemm.cuh -- FP64 tensor-core (DMMA, mma.sync.m8n8k4.f64) GEMM and the dense factorisation built on it.
+//
+// Replaces ksvd! (src/la_helper.jl:8-34, called at src/optimize.jl:291/293: "O(Nm^2)" thin SVD of Jct) by
+//   G = J J'            dgemm_nt, lower tiles only (SYRK)            flops m(m+1)N, FP64 tensor pipe
+//   G = L L'            blocked right-looking Cholesky (in-shared-memory diagonal blocks + DMMA panel/trailing updates)
+//   L^-T (and L^-1)     blocked triangular inverse from the diagonal-block inverses, DMMA
+// (the projector, the multipliers and NR's D0 = L^-1 are all expressed through L.)
+//
+// There is no tcgen05 FP64 MMA kind; mma.sync.m8n8k4.f64 (SASS: DMMA.8x8x4) is the FP64 tensor path on sm_100a.
+// One GEMM shape serves everything:  C[M x N] (op)= A[M x K] * B[N x K]'   with A, B, C row-major ("NT").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lfpsqp {
+
+enum GemmMode { GEMM_ASSIGN = 0, GEMM_SUB = 1, GEMM_ASSIGN_NEG = 2 };
+
+constexpr int GM_BM = 128, GM_BK = 16, GM_LD = 20 /* BK + 4: conflict-free 64-bit fragment loads */, GM_STAGES = 3;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool pred) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = pred ? 16 : 0;  // src-size 0 => zero-fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// C (op)= A * B'.  BN in {128, 64}.  256 threads = 8 warps as 2 (M) x 4 (N): warp tile 64 x (BN/4).
+// lower_only: skip tiles strictly above the diagonal (SYRK / symmetric trailing update); tile (bi,bj) kept iff bi*BM+BM > bj*BN.
+// ksplit > 1: split-K, slice z writes its partial into C + z*c_split_stride (ASSIGN only); the caller reduces.
+// Requirements: lda, ldb even; A, B 16-byte aligned; K arbitrary (zero-filled), M, N arbitrary (predicated).
+template <int BN>
+__global__ void __launch_bounds__(256) dgemm_nt_kernel(int M, int N, int K, const double *__restrict__ A, int64_t lda,
+                                                       const double *__restrict__ B, int64_t ldb, double *__restrict__ C,
+                                                       int64_t ldc, int mode, int lower_only, int ksplit,
+                                                       int64_t c_split_stride) {
+  constexpr int BM = GM_BM, BK = GM_BK, LD = GM_LD, ST = GM_STAGES;
+  constexpr int WN = BN / 4;       // warp tile width
+  constexpr int NF = WN / 8;       // B fragments per warp per k4 step
+  extern __shared__ double gsm[];
+  double *As = gsm;                          // ST x BM x LD
+  double *Bs = gsm + (size_t)ST * BM * LD;   // ST x BN x LD
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (lower_only && (bi * BM + BM <= bj * BN)) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp >> 2, wn = warp & 3;   // 2 x 4
+  const int row0 = bi * BM, col0 = bj * BN;
+  // K range of this split
+  int kchunks = (K + BK - 1) / BK;
+  int per = (kchunks + ksplit - 1) / ksplit;
+  int kc0 = blockIdx.z * per, kc1 = min(kchunks, kc0 + per);
+  if (kc0 >= kc1 && ksplit > 1) { kc1 = kc0; }
+  double acc[8][NF][2];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < NF; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+  auto load_stage = [&](int stage, int kc) {
+    const int k0 = kc * BK;
+    // A tile: BM rows x 8 chunks of 16 B
+#pragma unroll
+    for (int q = 0; q < (BM * 8) / 256; q++) {
+      int idx = tid + q * 256, r = idx >> 3, ch = idx & 7;
+      int gr = row0 + r, gk = k0 + ch * 2;
+      bool ok = (gr < M) && (gk < K);
+      const double *src = ok ? (A + (int64_t)gr * lda + gk) : A;
+      cp_async16(As + ((size_t)stage * BM + r) * LD + ch * 2, src, ok);
+    }
+#pragma unroll
+    for (int q = 0; q < (BN * 8) / 256; q++) {
+      int idx = tid + q * 256, r = idx >> 3, ch = idx & 7;
+      int gr = col0 + r, gk = k0 + ch * 2;
+      bool ok = (gr < N) && (gk < K);
+      const double *src = ok ? (B + (int64_t)gr * ldb + gk) : B;
+      cp_async16(Bs + ((size_t)stage * BN + r) * LD + ch * 2, src, ok);
+    }
+  };
+
+  const int nk = kc1 - kc0;
+  for (int s = 0; s < ST - 1; s++) {
+    if (s < nk) load_stage(s, kc0 + s);
+    cp_async_commit();
+  }
+  for (int it = 0; it < nk; it++) {
+    cp_async_wait<ST - 2>();
+    __syncthreads();
+    {  // prefetch stage it+ST-1 (its buffer was consumed in iteration it-1)
+      int nx = it + ST - 1;
+      if (nx < nk) load_stage(nx % ST, kc0 + nx);
+      cp_async_commit();
+    }
+    const double *as = As + (size_t)(it % ST) * BM * LD + (size_t)(wm * 64) * LD;
+    const double *bs = Bs + (size_t)(it % ST) * BN * LD + (size_t)(wn * WN) * LD;
+#pragma unroll
+    for (int k4 = 0; k4 < BK / 4; k4++) {
+      double af[8], bf[NF];
+#pragma unroll
+      for (int i = 0; i < 8; i++) af[i] = as[(size_t)(i * 8 + (lane >> 2)) * LD + k4 * 4 + (lane & 3)];
+#pragma unroll
+      for (int j = 0; j < NF; j++) bf[j] = bs[(size_t)(j * 8 + (lane >> 2)) * LD + k4 * 4 + (lane & 3)];
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < NF; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  cp_async_wait<0>();
+  // epilogue: thread holds C[row = lane/4][col = 2*(lane%4) + {0,1}] of each 8x8 atom
+  double *Cz = C + (int64_t)blockIdx.z * c_split_stride;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    int r = row0 + wm * 64 + i * 8 + (lane >> 2);
+    if (r >= M) continue;
+#pragma unroll
+    for (int j = 0; j < NF; j++) {
+      int c = col0 + wn * WN + j * 8 + 2 * (lane & 3);
+      double *p = Cz + (int64_t)r * ldc + c;
+      if (c + 1 < N) {
+        double2 v;
+        if (mode == GEMM_ASSIGN) v = make_double2(acc[i][j][0], acc[i][j][1]);
+        else if (mode == GEMM_ASSIGN_NEG) v = make_double2(-acc[i][j][0], -acc[i][j][1]);
+        else { double2 o = *reinterpret_cast<double2 *>(p); v = make_double2(o.x - acc[i][j][0], o.y - acc[i][j][1]); }
+        *reinterpret_cast<double2 *>(p) = v;
+      } else if (c < N) {
+        if (mode == GEMM_ASSIGN) p[0] = acc[i][j][0];
+        else if (mode == GEMM_ASSIGN_NEG) p[0] = -acc[i][j][0];
+        else p[0] -= acc[i][j][0];
+      }
+    }
+  }
+}
+
+template <int BN> constexpr size_t dgemm_smem_bytes() { return (size_t)GM_STAGES * (GM_BM + BN) * GM_LD * sizeof(double); }
+
+// ------------------------------------------------------------------ diagonal block: in-shared-memory Cholesky + inverse
+// One CTA factors the NB x NB diagonal block of A (row-major, lda) in shared memory, writes L_jj back (zeros above
+// the diagonal) and D = L_jj^-1 (row-major NB x NB, zeros above the diagonal) to Dout.  nb_act <= NB rows are active.
+// flag[0] is set to 1 when a pivot is not > thresh (rank deficiency, cf. optimize.jl:297-302).
+template <int NB>
+__global__ void __launch_bounds__(256) potf2_inv_kernel(double *A, int64_t lda, int nb_act, double *Dout,
+                                                        const double *thresh_p, int *flag) {
+  extern __shared__ double psm[];
+  double (*Ls)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(psm);
+  double (*Ds)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(psm + NB * (NB + 1));
+  const int tid = threadIdx.x;
+  const double thresh = thresh_p[0];
+  for (int e = tid; e < NB * NB; e += 256) {
+    int r = e / NB, c = e % NB;
+    Ls[r][c] = (r < nb_act && c < nb_act) ? A[(int64_t)r * lda + c] : (r == c ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  for (int k = 0; k < nb_act; k++) {
+    double piv = Ls[k][k];
+    __syncthreads();
+    if (!(piv > thresh)) { if (tid == 0) flag[0] = 1; piv = (piv > 0.0) ? piv : 1.0; }
+    double d = sqrt(piv);
+    if (tid == 0) Ls[k][k] = d;
+    for (int i = k + 1 + tid; i < nb_act; i += 256) Ls[i][k] = Ls[i][k] / d;
+    __syncthreads();
+    // trailing update of the lower triangle: A[i][j] -= L[i][k] L[j][k], k < j <= i
+    int rem = nb_act - k - 1;
+    for (int e = tid; e < rem * rem; e += 256) {
+      int i = k + 1 + e / rem, j = k + 1 + e % rem;
+      if (j <= i) Ls[i][j] -= Ls[i][k] * Ls[j][k];
+    }
+    __syncthreads();
+  }
+  // D = L^-1 : column c by forward substitution, one column per thread
+  for (int c = tid; c < NB; c += 256) {
+    for (int i = 0; i < NB; i++) {
+      double s = (i == c) ? 1.0 : 0.0;
+      if (i < c) { Ds[i][c] = 0.0; continue; }
+      for (int t = c; t < i; t++) s -= Ls[i][t] * Ds[t][c];
+      Ds[i][c] = s / Ls[i][i];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < NB * NB; e += 256) {
+    int r = e / NB, c = e % NB;
+    if (r < nb_act && c < nb_act) A[(int64_t)r * lda + c] = (c <= r) ? Ls[r][c] : 0.0;
+    Dout[e] = (r < nb_act && c < nb_act) ? Ds[r][c] : 0.0;
+  }
+}
+
+// thresh[0] = max(eps_rank^2, 1e-14 * max_i G[i][i])  (the Gram-form stand-in for "sigma_j < eps_rank", optimize.jl:297-302)
+__global__ void __launch_bounds__(256) diag_thresh_kernel(const double *G, int64_t ldg, int m, double eps_rank, double *thresh) {
+  __shared__ double red[256];
+  double mx = 0.0;
+  for (int i = threadIdx.x; i < m; i += 256) mx = fmax(mx, G[(int64_t)i * ldg + i]);
+  red[threadIdx.x] = mx;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) { if (threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]); __syncthreads(); }
+  if (threadIdx.x == 0) thresh[0] = fmax(eps_rank * eps_rank, 1e-14 * red[0]);
+}
+
+// dst (cols x rows, ldd) = src (rows x cols, lds)'  -- 32x32 tiles through shared memory
+__global__ void __launch_bounds__(256) transpose_kernel(const double *__restrict__ src, int64_t lds, double *__restrict__ dst,
+                                                        int64_t ldd, int rows, int cols) {
+  __shared__ double t[32][33];
+  int bx = blockIdx.x * 32, by = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    int gr = by + r, gc = bx + tx;
+    t[r][tx] = (gr < rows && gc < cols) ? src[(int64_t)gr * lds + gc] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    int gr = bx + r, gc = by + tx;  // dst row = src col
+    if (gr < cols && gc < rows) dst[(int64_t)gr * ldd + gc] = t[tx][r];
+  }
+}
+
+// zero the strict upper triangle of a row-major m x m matrix / copy a small block / set to zero
+__global__ void zero_upper_kernel(double *A, int64_t lda, int m) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)m * m) return;
+  int r = (int)(e / m), c = (int)(e % m);
+  if (c > r) A[(int64_t)r * lda + c] = 0.0;
+}
+// dst[c][r] = src[r][c] for r, c < nb_act ; src is an NB x NB row-major block
+__global__ void copy_block_T_kernel(const double *src, int NB, int nb_act, double *dst, int64_t ldd) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= NB * NB) return;
+  int r = e / NB, c = e % NB;
+  if (r < nb_act && c < nb_act) dst[(int64_t)c * ldd + r] = src[e];
+}
+
+}  // namespace lfpsqp

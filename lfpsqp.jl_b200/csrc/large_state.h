@@ -1,0 +1,54 @@
+// large_state.h -- host-side state of the large-n mode (owned by the ctx) and the communicator hooks.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <vector>
+#include "../../include/lfpsqp_b200.h"
+#include "large_ctrl.h"
+
+struct CommState {           // NCCL communicator of a column-sharded solve (comm.cu); world <= 1 means single GPU
+  void *nccl = nullptr;      // ncclComm_t
+  int rank = 0, world = 0;
+};
+
+struct LargeState {
+  int family = 0;
+  int64_t n = 0, n_loc = 0, col0 = 0, ldj = 0, ldm = 0;
+  int m = 0, sm_count = 148, world = 1, rank = 0;
+  cudaStream_t stream = nullptr;
+  lfpsqp_params prm;
+  CommState comm;
+  // family parameters (device)
+  const double *p_Q = nullptr, *p_A = nullptr, *p_b = nullptr, *p_xt = nullptr, *p_w = nullptr;
+  // matrices
+  double *J = nullptr, *G = nullptr, *XT = nullptr, *Linv = nullptr, *Dblk = nullptr, *tmp64 = nullptr, *thresh = nullptr,
+         *gemm_ws = nullptr, *Dnr = nullptr;
+  size_t gemm_ws_bytes = 0;
+  // n_loc vectors
+  double *x = nullptr, *xnew = nullptr, *xtil = nullptr, *g = nullptr, *d = nullptr, *nd = nullptr, *w0 = nullptr,
+         *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr, *hdiag = nullptr;
+  // m vectors (replicated on every rank)
+  double *cval = nullptr, *lam = nullptr, *tm = nullptr, *ty = nullptr, *tu = nullptr, *nr_t1 = nullptr, *nr_t2 = nullptr,
+         *nr_dc = nullptr;
+  double *cpart = nullptr;   // pass-2 partial column sums [nsplit][n_loc]
+  int nsplit = 1, rows_per_split = 1;
+  double *lp = nullptr, *gpart = nullptr, *commbuf = nullptr;   // loop partials, generic partials [NSLOT][MAXP]
+  lfpsqp::LargeCtrl *ctrl = nullptr, *hctrl = nullptr;
+  int vgrid = 1, np_loop = 1, np_loop_raw = 1, cg_chunk = 2, pcg_chunk = 2;
+  cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr;
+  std::vector<void *> owned;
+  // counters
+  int64_t launches = 0, projcg_iters = 0, projcg_negcurv = 0, armijo_trials = 0, retract_outer = 0, retract_pcg = 0,
+          pp_backtracks = 0, newton_accepted = 0, factorizations = 0, f_evals = 0;
+  void reset_counters() {
+    launches = projcg_iters = projcg_negcurv = armijo_trials = retract_outer = retract_pcg = pp_backtracks = 0;
+    newton_accepted = factorizations = f_evals = 0;
+  }
+};
+
+// comm.cu
+void comm_allreduce(LargeState &S, double *buf, size_t count);                  // in-place sum over ranks
+void comm_allreduce_scalars(LargeState &S, unsigned summask, unsigned maxmask); // ctrl->s[k] for the masked slots
+void comm_allreduce_loop_slot(LargeState &S, int slot, int np);                 // lp[slot][0] = sum over ranks of sum_i lp[slot][i]
+void comm_allreduce_loop_slots_cg(LargeState &S, int par);                      // slots 1 and 2+par
+void comm_release(LargeState &S);

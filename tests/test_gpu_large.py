@@ -1,0 +1,157 @@
+"""GPU parity tests (large-n mode): DMMA Gram + Cholesky, streaming projection, projcg and full solves vs numpy / the
+CPU oracle on the same seeded inputs, through the C ABI."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    import lfpsqp.jl_b200 as L
+    L.default_context(0)
+    return L
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.mark.parametrize("n,m", [(512, 32), (1000, 130), (4096, 200), (2048, 64), (770, 1)])
+def test_factor_and_projection_vs_numpy(L, n, m):
+    # ksvd! replacement (la_helper.jl:8-34): G = J J', L = chol(G), L^-1 ; kgemv! pair (optimize.jl:306-307) ; multipliers (:333-343)
+    Q, A, b, xt, w, x0 = L.make_diagquad(n, m, seed=n + m, cond=100.0)
+    P = L.LargeProblem(L.families.diagquad(Q, A, b, xt, w))
+    J = Q * x0[None, :] + A
+    fac = P.factor(x0)
+    G = J @ J.T
+    Lc = np.linalg.cholesky(G)
+    assert fac["rank_deficient"] == 0
+    assert rel(np.tril(fac["G"]), np.tril(G)) < 1e-14
+    assert rel(np.tril(fac["L"]), Lc) < 1e-13
+    assert rel(fac["Linv"], np.linalg.inv(Lc)) < 1e-12
+    v = np.random.default_rng(3).standard_normal(n)
+    pv, lam = P.project(v)
+    u = np.linalg.solve(G, J @ v)
+    assert rel(pv, v - J.T @ u) < 1e-13 and rel(lam, u) < 1e-12
+    assert np.linalg.norm(J @ pv) < 1e-11 * np.linalg.norm(v)          # tangent: J P v = 0
+    pv2, _ = P.project(pv)
+    assert rel(pv2, pv) < 1e-13                                         # idempotent projector
+
+
+def test_projcg_properties(L):
+    # test/test_cg.jl:23-28 re-expressed: converged projected residual, iterate in the tangent space, KKT residual
+    n, m = 2048, 96
+    Q, A, b, xt, w, x0 = L.make_diagquad(n, m, seed=11, cond=1e3)
+    P = L.LargeProblem(L.families.diagquad(Q, A, b, xt, w))
+    J = Q * x0[None, :] + A
+    P.factor(x0, want=())
+    lam = np.random.default_rng(1).standard_normal(m) * 0.1
+    hd = w + Q.T @ lam
+    assert np.all(hd > 0)
+    for tol in (1e-6, 1e-10):
+        r = P.projcg(x0, lam=lam, tol=tol, maxit=10000)
+        assert r["status"] == 1 and r["nr"] < tol
+        x = r["sol"]
+        assert np.linalg.norm(J @ x) < 1e-10 * max(1.0, np.linalg.norm(x))
+        g = w * (x0 - xt)
+        Pm = lambda v: v - J.T @ np.linalg.solve(J @ J.T, J @ v)
+        bvec = Pm(-g)
+        assert np.linalg.norm(Pm(hd * x - bvec)) < max(10 * tol, 1e-9)
+    # indefinite Hessian => negative-curvature exit (test/test_cg.jl:39-54): |x| = 1, x'Hx <= 0, x tangent
+    lam2 = -50.0 * np.abs(np.random.default_rng(2).standard_normal(m))
+    hd2 = w + Q.T @ lam2
+    if np.any(hd2 < 0):
+        r = P.projcg(x0, lam=lam2, tol=1e-20, maxit=10000)
+        if r["status"] == 2:
+            x = r["sol"]
+            assert np.isinf(r["nr"]) and abs(np.linalg.norm(x) - 1.0) < 1e-12
+            assert x @ (hd2 * x) <= 0.0 and np.linalg.norm(J @ x) < 1e-10
+
+
+@pytest.mark.parametrize("n,m", [(512, 32), (1000, 130), (4096, 200)])
+def test_diagquad_solve_vs_oracle(L, oracle, n, m):
+    Q, A, b, xt, w, x0 = L.make_diagquad(n, m, seed=1, cond=100.0)
+    fam = L.families.diagquad(Q, A, b, xt, w)
+    P = L.LargeProblem(fam)
+    x, obj, lam, info, st, status = P.solve(x0, L.LFPSQPParams(), return_stats=True)
+    ox, oobj, olam, ot, ost = oracle.optimize("diagquad", n, m, 0, x0, fam_params=fam.params)
+    assert status == 0 and int(info.condition) == ot["condition"] and abs(info.iter - ot["iter"]) <= 1
+    assert rel(x, ox) <= 1e-8 and abs(obj[-1] - oobj[-1]) <= 1e-10 * abs(oobj[-1])
+    assert rel(lam, olam) <= 1e-6
+    assert len(obj) == info.iter + 1
+    # feasibility to eps_c and the cached-factor counters
+    J = Q * x[None, :] + A
+    assert np.max(np.abs(0.5 * Q @ (x * x) + A @ x - b)) < 1e-6
+    assert st["factorizations"] == info.iter + 1
+
+
+def test_diagquad_solve_nr_vs_oracle(L, oracle):
+    n, m = 4096, 200
+    Q, A, b, xt, w, x0 = L.make_diagquad(n, m, seed=1, cond=100.0)
+    fam = L.families.diagquad(Q, A, b, xt, w)
+    P = L.LargeProblem(fam)
+    x, obj, lam, info, st, status = P.solve(x0, L.LFPSQPParams(do_project_retract=False), return_stats=True)
+    ox, oobj, olam, ot, ost = oracle.optimize("diagquad", n, m, 0, x0, fam_params=fam.params,
+                                              params=oracle.default_params(do_project_retract=0))
+    assert status == 0 and int(info.condition) == ot["condition"] and abs(info.iter - ot["iter"]) <= 1
+    assert rel(x, ox) <= 1e-8 and abs(obj[-1] - oobj[-1]) <= 1e-10 * abs(oobj[-1])
+    assert st["retract_outer"] == ost["retract_outer"]
+
+
+@pytest.mark.parametrize("npts", [32, 100])
+def test_thomson_solve_vs_oracle(L, oracle, npts):
+    rng = np.random.default_rng(6)
+    x0 = rng.standard_normal((npts, 3)); x0 /= np.linalg.norm(x0, axis=1, keepdims=True); x0 = x0.ravel()
+    P = L.LargeProblem(L.families.thomson(npts))
+    x, obj, lam, info, st, status = P.solve(x0, L.LFPSQPParams(), return_stats=True)
+    ox, oobj, olam, ot, ost = oracle.optimize("thomson", 3 * npts, npts, 0, x0)
+    assert status == 0 and int(info.condition) == ot["condition"] and abs(info.iter - ot["iter"]) <= 1
+    assert rel(x, ox) <= 1e-8 and abs(obj[-1] - oobj[-1]) <= 1e-10 * abs(oobj[-1])
+    assert np.max(np.abs(np.sum(x.reshape(-1, 3) ** 2, axis=1) - 1.0)) < 1e-6
+
+
+def test_large_matches_batched_mode(L):
+    # the two execution modes implement the same algorithm: same problem through both
+    n, m = 64, 4
+    Q, A, b, xt, w, x0 = L.make_diagquad(n, m, seed=5, cond=50.0)
+    fam = L.families.diagquad(Q, A, b, xt, w)
+    xa, obja, lama, infoa = L.optimize(fam.f, fam.c, x0, m)
+    xb, objb, lamb, infob = L.LargeProblem(fam).solve(x0)
+    assert infoa.condition == infob.condition and infoa.iter == infob.iter
+    assert rel(xa, xb) < 1e-9 and abs(obja[-1] - objb[-1]) <= 1e-10 * abs(objb[-1])
+
+
+def test_full_size_properties_c5(L):
+    # BASELINE config C5 (n=65536, m=2048) through size-independent properties: projector idempotence/tangency,
+    # fixed-K projcg runs K iterations, and J J' = L L' checked through random probes (no 2 GB host copies)
+    import torch
+    n, m = 65536, 2048
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev); g.manual_seed(0)
+    Q = torch.randn((m, n), dtype=torch.float64, device=dev, generator=g) / np.sqrt(n)
+    A = torch.randn((m, n), dtype=torch.float64, device=dev, generator=g) / np.sqrt(n)
+    x0 = torch.randn(n, dtype=torch.float64, device=dev, generator=g)
+    xt = torch.randn(n, dtype=torch.float64, device=dev, generator=g)
+    w = torch.exp(torch.rand(n, dtype=torch.float64, device=dev, generator=g) * np.log(1e4))
+    b = 0.5 * Q @ (x0 * x0) + A @ x0
+    blob = torch.cat([Q.reshape(-1), A.reshape(-1), b, xt, w]).contiguous()
+    J = Q * x0[None, :] + A
+    del Q, A
+    fam = L.families.Family(L.families.DIAGQUAD, "diagquad", n, m, 0)
+    P = L.LargeProblem(fam, params_dev_ptr=blob.data_ptr())
+    x0h = x0.cpu().numpy()
+    fac = P.factor(x0h, want=("L",))
+    assert fac["rank_deficient"] == 0
+    Lh = torch.from_numpy(np.tril(fac["L"])).to(dev)
+    z = torch.randn(m, dtype=torch.float64, device=dev, generator=g)
+    lhs = Lh @ (Lh.T @ z); rhs = J @ (J.T @ z)
+    assert float(torch.linalg.norm(lhs - rhs) / torch.linalg.norm(rhs)) < 1e-12
+    v = np.random.default_rng(0).standard_normal(n)
+    pv, lam = P.project(v)
+    Jpv = (J @ torch.from_numpy(pv).to(dev)).cpu().numpy()
+    assert np.linalg.norm(Jpv) < 1e-10 * np.linalg.norm(v)
+    pv2, _ = P.project(pv)
+    assert rel(pv2, pv) < 1e-12
+    r = P.projcg(x0h, lam=np.zeros(m), tol=0.0, maxit=8, want_solution=False)
+    assert r["iters"] == 8 and r["status"] == 4
