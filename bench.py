@@ -114,6 +114,84 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def large_n_section(L, ctx, torch, dev, with_cpu):
+    """Secondary metric of BASELINE.json: large-n projcg iterations/s on config C5 (n=65536, m=2048 dense random
+    diagonal-quadratic equality constraints, definition pinned in DESIGN.md), fixed-K projcg (tol=0) through the
+    unit-level export, plus the FP64 DMMA Gram.  Inputs are generated on the device (2 GB of parameters)."""
+    n, m, K = 65536, 2048, 64
+    g = torch.Generator(device=dev); g.manual_seed(SEED)
+    Q = torch.randn((m, n), dtype=torch.float64, device=dev, generator=g) / np.sqrt(n)
+    A = torch.randn((m, n), dtype=torch.float64, device=dev, generator=g) / np.sqrt(n)
+    x0 = torch.randn(n, dtype=torch.float64, device=dev, generator=g)
+    xt = torch.randn(n, dtype=torch.float64, device=dev, generator=g)
+    w = torch.exp(torch.rand(n, dtype=torch.float64, device=dev, generator=g) * np.log(1e4))
+    b = 0.5 * Q @ (x0 * x0) + A @ x0
+    blob = torch.cat([Q.reshape(-1), A.reshape(-1), b, xt, w]).contiguous()
+    del Q, A
+    torch.cuda.synchronize()
+    fam = L.families.Family(L.families.DIAGQUAD, "diagquad", n, m, 0)
+    P = L.LargeProblem(fam, ctx, params_dev_ptr=blob.data_ptr())
+    x0h = x0.cpu().numpy()
+    lam0 = np.zeros(m)
+    gram_ms = []
+    for _ in range(3):
+        gram_ms.append(P.factor(x0h, want=())["gram_ms"])
+    gram_ms = float(np.min(gram_ms[1:]))
+    for _ in range(3):  # warm-up
+        P.projcg(x0h, lam=lam0, tol=0.0, maxit=8, chunk=16, want_solution=False)
+    per = []
+    launches = 0
+    for _ in range(5):
+        r = P.projcg(x0h, lam=lam0, tol=0.0, maxit=K, chunk=16, want_solution=False)
+        assert r["iters"] == K
+        per.append(r["ms"] / K)
+        launches = ctx.last_launches
+    ms_it = float(np.median(per))
+    bytes_it = 16.0 * m * n + 8.0 * m * m + 104.0 * n     # SURVEY.md 8(d): two passes over J + two triangular GEMVs + vector sweeps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    ach = bytes_it / (ms_it * 1e-3) / 1e9
+    out = {"metric": "large-n projcg iterations/s", "value": 1e3 / ms_it, "unit": "iterations/s",
+           "config": {"workload": "C5 large dense: n=65536, m=2048, c_i = 1/2 sum_j Q_ij x_j^2 + A_i.x - b_i, "
+                                  "f = 1/2 (x-xt)' diag(w) (x-xt), fixed K=%d projcg iterations (tol=0), 1 GPU" % K,
+                      "l2": "J alone is 1 GiB per pass (>> 126 MB L2)"},
+           "ms_per_iteration": ms_it, "gpu_launches_per_iteration": launches / K,
+           "roofline": {"bound": "hbm", "kernels": "rows_dot_kernel + cols_dot_kernel (+ tri_gemv, cg_update*)",
+                        "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                        "algorithmic_bytes_per_iteration": bytes_it, "traffic": None,
+                        "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"}}
+    try:
+        dmma = ctx.fp64_peak("dmma")
+        flops = float(m) * (m + 1) * n
+        out["gram"] = {"kernel": "dgemm_nt_kernel<128> (SYRK, lower tiles, mma.sync.m8n8k4.f64)", "ms": gram_ms, "flops": flops,
+                       "bound": "tensor", "achieved": flops / (gram_ms * 1e-3) / 1e12, "peak": dmma, "unit": "TFLOP/s",
+                       "frac": flops / (gram_ms * 1e-3) / 1e12 / dmma,
+                       "peak_source": "DMMA (mma.sync.m8n8k4.f64) microbenchmark measured in this run"}
+    except Exception as e:  # noqa
+        out["gram"] = {"error": str(e)}
+    if with_cpu:
+        # CPU baseline per phase (BASELINE.md section 3): the reference's projection is a GEMV pair over the n x m basis
+        nth = host_cores()
+        U = np.random.default_rng(0).standard_normal((m, n))     # same shape/bytes as the orthonormal basis (row-major J')
+        v = np.random.default_rng(1).standard_normal(n)
+        hd = np.ones(n)
+        t0 = time.perf_counter(); reps = 0
+        while time.perf_counter() - t0 < 4.0 or reps < 2:
+            Ad = hd * v; dAd = v @ Ad; rp = v + 0.5 * Ad
+            tt = U @ rp; gp = rp - U.T @ tt; beta = (rp @ gp) / max(dAd, 1e-300); v = beta * v - gp
+            v /= np.linalg.norm(v); reps += 1
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": reps / dt, "unit": "iterations/s", "cores": nth, "kind": "port",
+                               "sample": "%d projcg iterations (GEMV pair over the %dx%d basis + vector updates), numpy/OpenBLAS threads" % (reps, n, m)}
+        del U
+    del blob
+    return out
+
+
 def run_reference(args):
     """Reference arm: the reference's CPU implementation of the path = the oracle port (kind "port"), all host threads,
     same config/metric; each step is a bounded sample of the workload."""
@@ -155,6 +233,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-large", action="store_true", help="skip the secondary large-n (C5) section")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -311,6 +390,11 @@ def main():
                             "note": "algorithmic flops = the oracle's instrumented FP64 op count (mean per instance)"}
         except Exception as e:  # noqa
             line["fp64"] = {"error": str(e)}
+    if world == 1 and not args.skip_large:
+        try:
+            line["large_n"] = large_n_section(L, ctx, torch, dev, not args.no_cpu_baseline)
+        except Exception as e:  # noqa
+            line["large_n"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -1,0 +1,80 @@
+# LFPSQPB200.jl -- thin `ccall` layer over liblfpsqp_b200.so (include/lfpsqp_b200.h) keeping LFPSQP.jl's
+# `optimize(...)` method family and its `(x, obj_values, λ_kkt, term_info)` return (src/optimize.jl:13-114, :442).
+#
+# NOTE: Julia is not installed in the build image, so this file has never been executed; the identical call sequence
+# is exercised through the ctypes mirror `lfpsqp.jl_b200/api.py`.  No CUDA.jl, no array dispatch: plain pointers.
+module LFPSQPB200
+
+export optimize, optimize_batched, LFPSQPParams, TerminationInfo, DeviceFamily, rosenbrock, readme_equality,
+       readme_inequality, thomson, diagquad
+
+const lib = joinpath(@__DIR__, "..", "liblfpsqp_b200.so")
+
+@enum TerminationCondition f_tol x_tol kkt_tol max_iter armijo_error   # src/LFPSQP.jl:37-43
+
+# lfpsqp_params == LFPSQPParams (src/LFPSQP.jl:57-81), C layout
+Base.@kwdef struct LFPSQPParams
+    α::Float64 = 1.0;  β::Float64 = 0.0;  t_β::Int64 = 0;  s::Float64 = 0.5;  σ::Float64 = 1e-4
+    ϵ_c::Float64 = 1e-6;  ϵ_f::Float64 = 1e-6;  ϵ_x::Float64 = 0.0;  ϵ_kkt::Float64 = 1e-6;  ϵ_rank::Float64 = 1e-10
+    maxiter::Int64 = 10000;  maxiter_retract::Int64 = 100;  maxiter_pcg::Int64 = 100;  μ0::Float64 = 1e-2
+    disable_linesearch::Int32 = 0;  do_project_retract::Int32 = 1;  disp::Int32 = 1;  linesearch::Int32 = 0
+    do_newton::Int32 = 1;  _pad::Int32 = 0;  tn_maxiter::Int64 = 10000;  tn_κ::Float64 = 0.5;  callback_period::Int64 = 100
+end
+
+struct CTerm                      # lfpsqp_term (TerminationInfo + status bits in the enum's padding)
+    condition::Int32; status::Int32; f_diff::Float64; step_diff::Float64; kkt_diff::Float64; iter::Int64
+end
+
+struct TerminationInfo            # src/LFPSQP.jl:45-51
+    condition::TerminationCondition; f_diff::Float64; step_diff::Float64; kkt_diff::Float64; iter::Int64
+end
+
+# registered device family: id + parameter blob (replaces the closures f, c!, d!)
+struct DeviceFamily
+    id::Cint; n::Int64; m::Int64; p::Int64; params::Vector{Float64}; stride::Int64
+end
+rosenbrock() = DeviceFamily(0, 2, 0, 0, Float64[], 0)
+readme_equality(n=50) = DeviceFamily(1, n, 1, 0, Float64[], 0)
+readme_inequality(coeff::Vector{Float64}) = DeviceFamily(2, length(coeff), 0, 1, coeff, 0)
+readme_inequality(coeff::Matrix{Float64}) = DeviceFamily(2, size(coeff, 1), 0, 1, vec(coeff), size(coeff, 1))  # n x B
+thomson(N) = DeviceFamily(3, 3N, N, 0, Float64[], 0)
+diagquad(Q, A, b, xt, w) = DeviceFamily(4, size(Q, 2), size(Q, 1), 0,
+                                        vcat(vec(permutedims(Q)), vec(permutedims(A)), b, xt, w), 0)  # row-major Q, A
+
+const ctx = Ref{Ptr{Cvoid}}(C_NULL)
+function context()
+    if ctx[] == C_NULL
+        rc = ccall((:lfpsqp_ctx_create, lib), Cint, (Cint, Ptr{Ptr{Cvoid}}), 0, ctx)
+        rc == 0 || error(unsafe_string(ccall((:lfpsqp_last_error, lib), Cstring, (Ptr{Cvoid},), C_NULL)))
+    end
+    ctx[]
+end
+check(rc) = rc == 0 || error(unsafe_string(ccall((:lfpsqp_last_error, lib), Cstring, (Ptr{Cvoid},), ctx[])))
+
+"B independent instances: X0 is n x B (column-major, one instance per column)."
+function optimize_batched(fam::DeviceFamily, X0::Matrix{Float64}, xl, xu, param::LFPSQPParams=LFPSQPParams(); history::Int=64)
+    n, B = size(X0); me = fam.m + fam.p
+    x = Matrix{Float64}(undef, n, B); obj = Matrix{Float64}(undef, history, B); len = Vector{Int64}(undef, B)
+    λ = Matrix{Float64}(undef, me, B); term = Vector{CTerm}(undef, B)
+    pl = isnothing(xl) ? Ptr{Float64}(C_NULL) : pointer(xl); pu = isnothing(xu) ? Ptr{Float64}(C_NULL) : pointer(xu)
+    GC.@preserve X0 xl xu x obj len λ term fam begin
+        check(ccall((:lfpsqp_solve_batched, lib), Cint,
+                    (Ptr{Cvoid}, Cint, Int64, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64},
+                     Ptr{Float64}, Ref{LFPSQPParams}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int64}, Ptr{Float64},
+                     Ptr{CTerm}, Ptr{Cvoid}),
+                    context(), fam.id, n, fam.m, fam.p, B, fam.params, fam.stride, X0, pl, pu, param, x, obj, history,
+                    len, λ, term, C_NULL))
+    end
+    x, obj, len, λ, term
+end
+
+# optimize(f, c!, d!, x0, xl, xu, m, p[, param])  (src/optimize.jl:83) -- f, c!, d! are replaced by the family handle
+function optimize(fam::DeviceFamily, x0::Vector{Float64}, xl, xu, param::LFPSQPParams=LFPSQPParams())
+    x, obj, len, λ, term = optimize_batched(fam, reshape(x0, :, 1), xl, xu, param; history=param.maxiter + 1)
+    t = term[1]
+    t.iter == param.maxiter && @warn "Maximum # of outer iterations reached"          # optimize.jl:438-440
+    x[:, 1], obj[1:len[1], 1], λ[:, 1], TerminationInfo(TerminationCondition(t.condition), t.f_diff, t.step_diff, t.kkt_diff, t.iter)
+end
+optimize(fam::DeviceFamily, x0::Vector{Float64}, param::LFPSQPParams=LFPSQPParams()) = optimize(fam, x0, nothing, nothing, param)
+
+end # module
