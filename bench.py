@@ -114,23 +114,33 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def large_n_section(L, ctx, torch, dev, with_cpu):
+def large_n_section(L, ctx, torch, dev, with_cpu, dist=None, rank=0, world=1):
     """Secondary metric of BASELINE.json: large-n projcg iterations/s on config C5 (n=65536, m=2048 dense random
     diagonal-quadratic equality constraints, definition pinned in DESIGN.md), fixed-K projcg (tol=0) through the
-    unit-level export, plus the FP64 DMMA Gram.  Inputs are generated on the device (2 GB of parameters)."""
+    unit-level export, plus the FP64 DMMA Gram.  Inputs are generated on the device (2 GB of parameters).
+    With world > 1 the instance is column-sharded (strong scaling): NCCL all-reduces the Gram, J v and the CG scalars."""
+    from lfpsqp.jl_b200 import dist as D
     n, m, K = 65536, 2048, 64
-    g = torch.Generator(device=dev); g.manual_seed(SEED)
-    Q = torch.randn((m, n), dtype=torch.float64, device=dev, generator=g) / np.sqrt(n)
-    A = torch.randn((m, n), dtype=torch.float64, device=dev, generator=g) / np.sqrt(n)
-    x0 = torch.randn(n, dtype=torch.float64, device=dev, generator=g)
-    xt = torch.randn(n, dtype=torch.float64, device=dev, generator=g)
-    w = torch.exp(torch.rand(n, dtype=torch.float64, device=dev, generator=g) * np.log(1e4))
+    col0, nloc = D.column_range(n, world, rank)
+    if world > 1:
+        D.init_comm(ctx, dist)
+    g = torch.Generator(device=dev); g.manual_seed(SEED)     # same stream on every rank; each keeps its column shard
+
+    def shard_rand():
+        full = torch.randn((m, n), dtype=torch.float64, device=dev, generator=g) / np.sqrt(n)
+        return full[:, col0:col0 + nloc].contiguous()
+    Q = shard_rand(); A = shard_rand()
+    x0 = torch.randn(n, dtype=torch.float64, device=dev, generator=g)[col0:col0 + nloc].contiguous()
+    xt = torch.randn(n, dtype=torch.float64, device=dev, generator=g)[col0:col0 + nloc]
+    w = torch.exp(torch.rand(n, dtype=torch.float64, device=dev, generator=g) * np.log(1e4))[col0:col0 + nloc]
     b = 0.5 * Q @ (x0 * x0) + A @ x0
+    if world > 1:
+        dist.all_reduce(b)
     blob = torch.cat([Q.reshape(-1), A.reshape(-1), b, xt, w]).contiguous()
     del Q, A
     torch.cuda.synchronize()
     fam = L.families.Family(L.families.DIAGQUAD, "diagquad", n, m, 0)
-    P = L.LargeProblem(fam, ctx, params_dev_ptr=blob.data_ptr())
+    P = L.LargeProblem(fam, ctx, col0=col0, n_loc=nloc, n_global=n, params_dev_ptr=blob.data_ptr())
     x0h = x0.cpu().numpy()
     lam0 = np.zeros(m)
     gram_ms = []
@@ -142,12 +152,17 @@ def large_n_section(L, ctx, torch, dev, with_cpu):
     per = []
     launches = 0
     for _ in range(5):
+        if world > 1:
+            dist.barrier()
         r = P.projcg(x0h, lam=lam0, tol=0.0, maxit=K, chunk=16, want_solution=False)
         assert r["iters"] == K
-        per.append(r["ms"] / K)
+        ms = r["ms"]
+        if world > 1:   # device time, max over ranks
+            t = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        per.append(ms / K)
         launches = ctx.last_launches
     ms_it = float(np.median(per))
-    bytes_it = 16.0 * m * n + 8.0 * m * m + 104.0 * n     # two passes over J + two triangular GEMVs + vector sweeps
+    bytes_it = 16.0 * m * nloc + 8.0 * m * m + 104.0 * nloc   # per GPU; SURVEY.md 8(d): two passes over J + two triangular GEMVs + vector sweeps
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -157,16 +172,17 @@ def large_n_section(L, ctx, torch, dev, with_cpu):
     ach = bytes_it / (ms_it * 1e-3) / 1e9
     out = {"metric": "large-n projcg iterations/s", "value": 1e3 / ms_it, "unit": "iterations/s",
            "config": {"workload": "C5 large dense: n=65536, m=2048, c_i = 1/2 sum_j Q_ij x_j^2 + A_i.x - b_i, "
-                                  "f = 1/2 (x-xt)' diag(w) (x-xt), fixed K=%d projcg iterations (tol=0), 1 GPU" % K,
+                                  "f = 1/2 (x-xt)' diag(w) (x-xt), fixed K=%d projcg iterations (tol=0), column-sharded over %d GPU(s)" % (K, world),
+                      "scaling": "strong (total work fixed, J and x sharded by columns)",
                       "l2": "J alone is 1 GiB per pass (>> 126 MB L2)"},
            "ms_per_iteration": ms_it, "gpu_launches_per_iteration": launches / K,
            "roofline": {"bound": "hbm", "kernels": "rows_dot_kernel + cols_dot_kernel (+ tri_gemv, cg_update*)",
                         "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                        "algorithmic_bytes_per_iteration": bytes_it, "traffic": None,
+                        "algorithmic_bytes_per_iteration_per_gpu": bytes_it, "traffic": None,
                         "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"}}
     try:
         dmma = ctx.fp64_peak("dmma")
-        flops = float(m) * (m + 1) * n
+        flops = float(m) * (m + 1) * nloc
         out["gram"] = {"kernel": "dgemm_nt_kernel<128> (SYRK, lower tiles, mma.sync.m8n8k4.f64)", "ms": gram_ms, "flops": flops,
                        "bound": "tensor", "achieved": flops / (gram_ms * 1e-3) / 1e12, "peak": dmma, "unit": "TFLOP/s",
                        "frac": flops / (gram_ms * 1e-3) / 1e12 / dmma,
@@ -390,9 +406,10 @@ def main():
                             "note": "algorithmic flops = the oracle's instrumented FP64 op count (mean per instance)"}
         except Exception as e:  # noqa
             line["fp64"] = {"error": str(e)}
-    if world == 1 and not args.skip_large:
+    if not args.skip_large:
         try:
-            line["large_n"] = large_n_section(L, ctx, torch, dev, not args.no_cpu_baseline)
+            line["large_n"] = large_n_section(L, ctx, torch, dev, (not args.no_cpu_baseline) and world == 1 and rank == 0,
+                                              dist, rank, world)
         except Exception as e:  # noqa
             line["large_n"] = {"error": repr(e)}
     if rank == 0:

@@ -146,6 +146,13 @@ int lfpsqp_large_project(lfpsqp_ctx *ctx, const double *v_loc, double *v_out_loc
 int lfpsqp_large_projcg(lfpsqp_ctx *ctx, const double *x_loc, const double *lam, double tol, int64_t maxit, int chunk,
                         double *sol_out_loc, int64_t *iters, double *nr, int *status, double *ms);
 
+/* Communicator of the column-sharded large-n mode: one process per GPU, NCCL (bound with dlopen so the process shares
+ * the libnccl.so.2 that e.g. torch.distributed loaded; nccl_lib_path may be NULL).  Rank 0 creates the 128-byte unique
+ * id, the host program broadcasts it (any transport), every rank calls lfpsqp_comm_init BEFORE lfpsqp_large_setup. */
+int lfpsqp_comm_unique_id(void *out128, const char *nccl_lib_path);
+int lfpsqp_comm_init(lfpsqp_ctx *ctx, int rank, int world, const void *unique_id128, const char *nccl_lib_path);
+int lfpsqp_comm_destroy(lfpsqp_ctx *ctx);
+
 /* Roofline denominators that MEASURED_PEAKS.json does not carry: measured FP64 peak of this GPU in TFLOP/s.
  * which: 0 = DFMA (vector pipe), 1 = DMMA (mma.sync.m8n8k4.f64 tensor pipe). */
 int lfpsqp_bench_fp64_peak(lfpsqp_ctx *ctx, int which, double *tflops);

@@ -87,6 +87,7 @@ extern "C" void lfpsqp_ctx_destroy(lfpsqp_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   lfpsqp_large_release(c);
+  lfpsqp_comm_destroy(c);
   for (void *b : c->bufs) if (b) cudaFree(b);
   if (c->work_counter) cudaFree(c->work_counter);
   if (c->ev0) cudaEventDestroy(c->ev0);

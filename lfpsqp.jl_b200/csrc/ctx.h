@@ -9,6 +9,11 @@
 
 struct LargeState;  // large-n mode workspace (large.cu)
 
+struct CommState {           // NCCL communicator of a column-sharded solve (comm.cu); world <= 1 means single GPU
+  void *nccl = nullptr;      // ncclComm_t
+  int rank = 0, world = 0;
+};
+
 struct lfpsqp_ctx {
   int device = 0, sm_count = 148, smem_optin = 232448;
   cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -21,6 +26,7 @@ struct lfpsqp_ctx {
   std::vector<void *> bufs;  // grow-only device arena, one slot per role (no allocation inside solve loops)
   std::vector<size_t> caps;
   LargeState *large = nullptr;
+  CommState comm;
 
   int fail(int code, const char *fmt, ...);
   int cuda_fail(cudaError_t e, const char *what);

@@ -33,10 +33,11 @@ template <class F>
 static void vec(LargeState &S, int64_t n, F f, int s0 = 0, int nsum = 0, int domax = 0) {
   vec_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, f, S.gpart, s0, nsum, domax);
 }
-static void finalize(LargeState &S, unsigned summask, unsigned maxmask) {
+// repmask: slots computed from REPLICATED m-vectors (identical on every rank) -- not all-reduced
+static void finalize(LargeState &S, unsigned summask, unsigned maxmask, unsigned repmask = 0) {
   finalize_kernel<<<1, 256, 0, S.stream>>>(S.gpart, S.vgrid, summask, maxmask, S.ctrl);
   S.launches++;
-  if (S.world > 1) comm_allreduce_scalars(S, summask, maxmask);
+  if (S.world > 1 && ((summask | maxmask) & ~repmask)) comm_allreduce_scalars(S, summask & ~repmask, maxmask & ~repmask);
 }
 static int read_ctrl(lfpsqp_ctx *c, LargeState &S) {
   CK(cudaMemcpyAsync(S.hctrl, S.ctrl, sizeof(LargeCtrl), cudaMemcpyDeviceToHost, S.stream));
@@ -300,7 +301,7 @@ static int retract_pp(lfpsqp_ctx *c, LargeState &S, int *flag_out, int *it1, int
     fam_c_jac(S, S.J, cval, xnew);                                                       // :340
     // curtol = |c|_inf (slot 3 max), c.c (slot 0) ; g = xnew - xtilde, g.g (slot 1)
     vec(S, m, [=] __device__(int64_t a, double *acc) { double v = cval[a]; acc[0] += v * v; acc[3] = fmax(acc[3], fabs(v)); }, 0, 1, 1);
-    finalize(S, 1u, 8u);
+    finalize(S, 1u, 8u, 1u | 8u);
     if (read_ctrl(c, S)) return -1;
     double curtol = S.hctrl->s[3], cc = S.hctrl->s[0];
     if (curtol < prm.eps_c) break;                                                       // :359-361
@@ -347,7 +348,7 @@ static int retract_pp(lfpsqp_ctx *c, LargeState &S, int *flag_out, int *it1, int
     fam_c_jac(S, nullptr, cval, xnew);                                                    // :392
     vec(S, m, [=] __device__(int64_t a, double *acc) { double v = cval[a]; acc[0] += v * v; }, 2, 1);   // slot 2 only
     S.launches += 2;
-    finalize(S, 7u, 0);
+    finalize(S, 7u, 0, 4u);
     if (read_ctrl(c, S)) return -1;
     double ar_dot = -S.hctrl->s[0], dist2 = S.hctrl->s[1], ccnew = S.hctrl->s[2];
     double alpha = 1.0;
@@ -385,7 +386,7 @@ static int retract_nr(lfpsqp_ctx *c, LargeState &S, int *flag_out, int *it1) {
   int i = 0;
   while (i < S.prm.maxiter_retract) {
     vec(S, m, [=] __device__(int64_t a, double *acc) { acc[3] = fmax(acc[3], fabs(cval[a])); }, 0, 0, 1);
-    finalize(S, 0, 8u);
+    finalize(S, 0, 8u, 8u);
     if (read_ctrl(c, S)) return -1;
     if (S.hctrl->s[3] < S.prm.eps_c) break;                                              // :135
     rows_dot(S, D, ldm, m, m, cval, t1, 0);                                              // D c
@@ -406,7 +407,7 @@ static int retract_nr(lfpsqp_ctx *c, LargeState &S, int *flag_out, int *it1) {
         double s = 0.0; for (int k = 0; k < ns; k++) s += cp[(int64_t)k * m + a];
         t2[a] = s; acc[0] += s * dcv[a];
       }, 0, 1);
-      finalize(S, 1u, 0);
+      finalize(S, 1u, 0, 1u);
       rows_dot(S, D, ldm, m, m, dcv, S.tm, 0);
       double *tmv = S.tm;
       vec(S, m, [=] __device__(int64_t a, double *) { t1[a] -= tmv[a]; });
@@ -555,16 +556,14 @@ extern "C" int lfpsqp_large_setup(lfpsqp_ctx *c, int family, int64_t n_global, i
     return c->fail(LFPSQP_ERR_FAMILY, "large-n mode supports the DIAGQUAD and THOMSON families");
   if (n_global < 1 || m < 0 || n_loc < 1 || col0 < 0 || col0 + n_loc > n_global || m > n_global)
     return c->fail(LFPSQP_ERR_ARG, "bad sizes for large-n setup");
+  if (c->comm.world <= 1 && n_loc != n_global) return c->fail(LFPSQP_ERR_ARG, "a column shard needs a communicator (lfpsqp_comm_init)");
   if (family == LFPSQP_FAM_THOMSON && (n_global % 3 || m != n_global / 3 || n_loc != n_global))
     return c->fail(LFPSQP_ERR_FAMILY, "THOMSON needs n = 3 m and runs on one GPU (its callbacks need all of x)");
   if (m > 16384) return c->fail(LFPSQP_ERR_ARG, "m too large for the replicated factor");
-  // keep the communicator across setups
-  LargeState *old = c->large; CommState comm;
-  if (old) { comm = old->comm; old->comm = CommState(); }
   lfpsqp_large_release(c);
   LargeState *Sp = new LargeState(); LargeState &S = *Sp;
   c->large = Sp;
-  S.comm = comm; S.world = comm.world > 0 ? comm.world : 1; S.rank = comm.rank;
+  S.comm = &c->comm; S.world = c->comm.world > 1 ? c->comm.world : 1; S.rank = c->comm.rank;
   if (S.world > 1 && family == LFPSQP_FAM_THOMSON) return c->fail(LFPSQP_ERR_FAMILY, "THOMSON is single-GPU");
   S.family = family; S.n = n_global; S.n_loc = n_loc; S.col0 = col0; S.m = (int)m; S.stream = c->stream;
   S.sm_count = c->sm_count; S.ldj = up2(n_loc); S.ldm = up2(std::max<int64_t>(m, 1));

@@ -5,11 +5,7 @@
 #include <vector>
 #include "../../include/lfpsqp_b200.h"
 #include "large_ctrl.h"
-
-struct CommState {           // NCCL communicator of a column-sharded solve (comm.cu); world <= 1 means single GPU
-  void *nccl = nullptr;      // ncclComm_t
-  int rank = 0, world = 0;
-};
+#include "ctx.h"
 
 struct LargeState {
   int family = 0;
@@ -17,7 +13,7 @@ struct LargeState {
   int m = 0, sm_count = 148, world = 1, rank = 0;
   cudaStream_t stream = nullptr;
   lfpsqp_params prm;
-  CommState comm;
+  CommState *comm = nullptr;
   // family parameters (device)
   const double *p_Q = nullptr, *p_A = nullptr, *p_b = nullptr, *p_xt = nullptr, *p_w = nullptr;
   // matrices
@@ -38,7 +34,7 @@ struct LargeState {
   cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr;
   std::vector<void *> owned;
   // counters
-  int64_t launches = 0, projcg_iters = 0, projcg_negcurv = 0, armijo_trials = 0, retract_outer = 0, retract_pcg = 0,
+  int64_t collectives = 0, launches = 0, projcg_iters = 0, projcg_negcurv = 0, armijo_trials = 0, retract_outer = 0, retract_pcg = 0,
           pp_backtracks = 0, newton_accepted = 0, factorizations = 0, f_evals = 0;
   void reset_counters() {
     launches = projcg_iters = projcg_negcurv = armijo_trials = retract_outer = retract_pcg = pp_backtracks = 0;
