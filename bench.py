@@ -365,7 +365,7 @@ def main():
     e2e_value = world * B * K / e2e_s
     clocks = sampler.finish(t_begin, t_end) if rank == 0 else None
 
-    # ---- roofline of the dominant (only) kernel: batched_warp_kernel<FamReadmeIneq>
+    # ---- roofline of the dominant (only) kernel: batched_reg_kernel<SepReadmeIneq,2,1,true> (register-resident warp solver)
     d_len_h = d_len.cpu().numpy()
     io_bytes = float(B * (n * 8 + n * 8 + n * 8 + 8 + 8 + 40) + 8 * np.minimum(d_len_h, H).sum())  # coeff,x0 in; x,len,lam,term,obj out
     kms = float(np.mean(kern_ms))
@@ -377,7 +377,7 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     achieved = io_bytes / (kms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "batched_warp_kernel<FamReadmeIneq>", "achieved": achieved, "peak": hbm_peak,
+    roofline = {"bound": "hbm", "kernel": "batched_reg_kernel<SepReadmeIneq,2,1,true>", "achieved": achieved, "peak": hbm_peak,
                 "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                 "kernel_ms": kms,
                 "note": "per-instance state lives on-chip; HBM only sees I/O (%.0f B/instance), so HBM is NOT the binding "

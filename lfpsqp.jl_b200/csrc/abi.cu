@@ -12,6 +12,8 @@
 
 using namespace lfpsqp;
 
+int launch_batched_reg(lfpsqp_ctx *c, lfpsqp::BatchedArgs &A);  // batched_reg.cu
+
 static_assert(sizeof(lfpsqp_params) == 160, "lfpsqp_params layout is part of the ABI");
 static_assert(sizeof(lfpsqp_term) == 40, "TerminationInfo is {Int32, pad, 3 x Float64, Int64} = 40 B");
 static_assert(sizeof(lfpsqp_stats) == 80, "lfpsqp_stats layout is part of the ABI");
@@ -217,6 +219,10 @@ int launch_tiny(lfpsqp_ctx *c, BatchedArgs &A) {
 
 int dispatch_batched(lfpsqp_ctx *c, BatchedArgs &A) {
   const int use_nr = A.prm.do_project_retract ? 0 : 1;
+  {  // separable families with a register-resident instantiation (batched_reg.cuh)
+    int rc = launch_batched_reg(c, A);
+    if (rc <= 0) return rc;
+  }
   switch (A.family) {
     case LFPSQP_FAM_ROSENBROCK:
       if (!A.ineq) return launch_tiny<FamRosenbrock, 2>(c, A);
