@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblfpsqp_b200.so")
+LIB_PATH = os.environ.get("LFPSQP_LIB_PATH") or os.path.join(_HERE, "liblfpsqp_b200.so")
 
 
 class CParams(C.Structure):  # lfpsqp_params == LFPSQPParams, src/LFPSQP.jl:57-81

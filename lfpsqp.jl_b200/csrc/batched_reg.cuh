@@ -58,6 +58,15 @@ LFPSQP_DEV double wmax(double v) {
   return v;
 }
 
+// two independent butterflies interleaved (same instruction count, half the dependent-latency chain)
+LFPSQP_DEV void wsum2(double &a, double &b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ta = __shfl_xor_sync(0xffffffffu, a, o), tb = __shfl_xor_sync(0xffffffffu, b, o);
+    a += ta; b += tb;
+  }
+}
+
 #define LF_UNROLL _Pragma("unroll")
 
 template <class Fam, int NPL, int ME, bool INEQ>
@@ -77,7 +86,7 @@ struct RegSolver {
   // instance state
   Vec x;
   double J[MEA][NPL], Lc[MEA][MEA], cval[MEA], lam[MEA];
-  double Dx[NPL], Dy[NPL], S[NPL], lamy[NPL];
+  double Dx[NPL], Dy[NPL], S[NPL], Sinv[NPL], lamy[NPL];
   double cvh[NPL], cvc[MEA];   // cvalaug = [h ; c] (retractions.jl:29), persistent across PP calls (stale-tail quirk)
   int st_projcg, st_negcurv, st_trials, st_rout, st_rpcg, st_bt, st_newton, st_fact, st_feval, status;
 
@@ -174,7 +183,8 @@ struct RegSolver {
   LFPSQP_DEV void calculate_h(double *out, const Vec &v) const {  // :112-122
     LF_UNROLL for (int k = 0; k < NPL; k++) {
       double q = bq[k], s = bs[k], r = br[k], dx = v.x[k] - r, dy = v.y[k] - r;
-      out[k] = valid[k] ? q * (dx * dx) + (1.0 - q * q) * v.x[k] + s * (dy * dy) - (1.0 - s * s) * v.y[k] - bt[k] : 0.0;
+      // padded elements have q = s = r = t = 0 and x = y = 0: the formula itself gives 0 there
+      out[k] = q * (dx * dx) + (1.0 - q * q) * v.x[k] + s * (dy * dy) - (1.0 - s * s) * v.y[k] - bt[k];
     }
   }
   LFPSQP_DEV void inequality_gradient(const Vec &v) {  // :125-141
@@ -182,8 +192,8 @@ struct RegSolver {
       double q = bq[k], s = bs[k], r = br[k];
       double dx = 2.0 * q * (v.x[k] - r) + (q == 0.0 ? 1.0 : 0.0);
       double dy = 2.0 * s * (v.y[k] - r) - (s == 0.0 ? 1.0 : 0.0);
-      double sv = sqrt(dx * dx + dy * dy);
-      S[k] = sv; Dx[k] = dx / sv; Dy[k] = dy / sv;
+      double sv = sqrt(dx * dx + dy * dy), inv = 1.0 / sv;   // one reciprocal instead of two divisions (<= 1 ulp apart)
+      S[k] = sv; Sinv[k] = inv; Dx[k] = dx * inv; Dy[k] = dy * inv;
     }
   }
   LFPSQP_DEV void y_retract(Vec &vn, const Vec &vb) const {  // retractions.jl:451-500
@@ -269,7 +279,7 @@ struct RegSolver {
         double wj = (ME > 0) ? coldot(u, k) : 0.0;
         v.x[k] -= Dx[k] * aa[k] + Dy[k] * Dy[k] * wj;
         v.y[k] -= Dy[k] * aa[k] - Dx[k] * Dy[k] * wj;
-        if (want_mult) lamy[k] = (-1.0 * Dx[k] / S[k]) * wj + aa[k] / S[k];
+        if (want_mult) lamy[k] = (-1.0 * Dx[k] * Sinv[k]) * wj + aa[k] * Sinv[k];
       }
     } else if (ME > 0) {
       rowdots(u, v.x); solveG(u);
@@ -287,6 +297,7 @@ struct RegSolver {
     int i = 0;
     const int N = INEQ ? 2 * NA : NA;
     int64_t lim = (int64_t)N + (INEQ ? NA + ME : ME); if (maxit < lim) lim = maxit;
+    double rg = dot(r, r);                                                      // r == g after every projection
     while (i < lim) {
       i++;
       hess_aux(Ad, dc);
@@ -297,7 +308,6 @@ struct RegSolver {
         st_negcurv++;
         break;
       }
-      double rg = dot(r, r);
       if (rg <= 0.0) break;                                                     // :87-89
       double alpha = rg / dAd;
       LF_UNROLL for (int k = 0; k < NPL; k++) {
@@ -306,13 +316,19 @@ struct RegSolver {
         if (INEQ) { xs.y[k] += alpha * dc.y[k]; double ty = r.y[k] + alpha * Ad.y[k]; rp.y[k] = ty; gp.y[k] = ty; }
       }
       project(gp, false);                                                       // :95-97
-      double beta = dot(rp, gp) / rg;
+      double rpgp = 0.0, gg = 0.0;                                              // rp.gp and gp.gp in one interleaved pass
+      LF_UNROLL for (int k = 0; k < NPL; k++) {
+        rpgp += rp.x[k] * gp.x[k]; gg += gp.x[k] * gp.x[k];
+        if (INEQ) { rpgp += rp.y[k] * gp.y[k]; gg += gp.y[k] * gp.y[k]; }
+      }
+      wsum2(rpgp, gg);
+      double beta = rpgp / rg;
       LF_UNROLL for (int k = 0; k < NPL; k++) {
         dc.x[k] = beta * dc.x[k] - gp.x[k]; r.x[k] = gp.x[k];
         if (INEQ) { dc.y[k] = beta * dc.y[k] - gp.y[k]; r.y[k] = gp.y[k]; }
       }
-      double nr = sqrt(dot(r, r));
-      if (nr < tol) break;                                                      // :107-111
+      rg = gg;                                                                  // next iteration's r.g (:84) == |g|^2
+      if (sqrt(gg) < tol) break;                                                // :103-111
     }
     st_projcg += i;
   }
@@ -346,26 +362,40 @@ struct RegSolver {
       }
       double cc = 0.0;
       LF_UNROLL for (int a = 0; a < ME; a++) cc += cvc[a] * cvc[a];
-      if (INEQ) hh = wsum(hh);
-      const double prev_obj = (hh + cc) + mu * wsum(gg);                // :366
+      if (INEQ) wsum2(hh, gg); else gg = wsum(gg);
+      const double prev_obj = (hh + cc) + mu * gg;                      // :366
       fullJ_mulT(gv, cvh, cvc, 1.0, mu);                                // :369
       r = gv; zero(dx); zero(pv);
-      // pcg! (:179-246), M! = copy
-      int pi = 0; double norm_res = INFINITY, rho = 1.0;
+      // pcg! (:179-246), M! = copy.  rho_k = r.r is reduced once per iteration (it is both norm(r)^2 of :235 and
+      // dot(z,r) of :213) together with J r, from which J p follows by the p-recurrence (J p = J r + beta J p_old).
+      int pi = 0; double norm_res = INFINITY, rho_prev = 1.0, rho, Jr[MEA], Jp[MEA];
+      {
+        double a0 = 0.0, b0 = 0.0;
+        LF_UNROLL for (int k = 0; k < NPL; k++) { a0 += r.x[k] * r.x[k]; if (INEQ) a0 += r.y[k] * r.y[k]; if (ME > 0) b0 += J[0][k] * r.x[k]; }
+        if (ME > 0) { wsum2(a0, b0); Jr[0] = b0; } else a0 = wsum(a0);
+        rho = a0;
+        LF_UNROLL for (int a = 1; a < ME; a++) { double s = 0.0; LF_UNROLL for (int k = 0; k < NPL; k++) s += J[a][k] * r.x[k]; Jr[a] = wsum(s); }
+        LF_UNROLL for (int a = 0; a < MEA; a++) Jp[a] = 0.0;
+      }
       while (norm_res > prm.eps_c && pi < prm.maxiter_pcg) {
-        double rho_prev = rho; rho = dot(r, r);
-        double beta = rho / rho_prev;
+        const double beta = rho / rho_prev;
         LF_UNROLL for (int k = 0; k < NPL; k++) { pv.x[k] = r.x[k] + beta * pv.x[k]; if (INEQ) pv.y[k] = r.y[k] + beta * pv.y[k]; }
-        double th[NPL], tc[MEA];
-        fullJ_mul(th, tc, pv);
+        LF_UNROLL for (int a = 0; a < ME; a++) Jp[a] = Jr[a] + beta * Jp[a];
+        double th[NPL];
+        if (INEQ) { LF_UNROLL for (int k = 0; k < NPL; k++) th[k] = S[k] * (Dx[k] * pv.x[k] + Dy[k] * pv.y[k]); }
         z = pv;
-        fullJ_mulT(z, th, tc, 1.0, mu);
-        double alpha = rho / dot(pv, z);
+        fullJ_mulT(z, th, Jp, 1.0, mu);
+        const double alpha = rho / dot(pv, z);
+        double a0 = 0.0, b0 = 0.0;
         LF_UNROLL for (int k = 0; k < NPL; k++) {
-          dx.x[k] += alpha * pv.x[k]; r.x[k] -= alpha * z.x[k];
-          if (INEQ) { dx.y[k] += alpha * pv.y[k]; r.y[k] -= alpha * z.y[k]; }
+          dx.x[k] += alpha * pv.x[k]; r.x[k] -= alpha * z.x[k]; a0 += r.x[k] * r.x[k];
+          if (ME > 0) b0 += J[0][k] * r.x[k];
+          if (INEQ) { dx.y[k] += alpha * pv.y[k]; r.y[k] -= alpha * z.y[k]; a0 += r.y[k] * r.y[k]; }
         }
-        norm_res = sqrt(dot(r, r));
+        if (ME > 0) { wsum2(a0, b0); Jr[0] = b0; } else a0 = wsum(a0);
+        LF_UNROLL for (int a = 1; a < ME; a++) { double s = 0.0; LF_UNROLL for (int k = 0; k < NPL; k++) s += J[a][k] * r.x[k]; Jr[a] = wsum(s); }
+        rho_prev = rho; rho = a0;
+        norm_res = sqrt(rho);
         pi++;
       }
       pcg_total += pi;
@@ -463,7 +493,7 @@ struct RegSolver {
       if (j < n) Fam::load(fc, j, ep[s]);
       x.x[s] = (j < n) ? A.x0[k * n + j] : 0.0;
       if (INEQ) x.y[s] = 0.0;
-      cvh[s] = 0.0; Dx[s] = 0.0; Dy[s] = 0.0; S[s] = 1.0; lamy[s] = 0.0;
+      cvh[s] = 0.0; Dx[s] = 0.0; Dy[s] = 0.0; S[s] = 1.0; Sinv[s] = 1.0; lamy[s] = 0.0;
     }
     LF_UNROLL for (int a = 0; a < MEA; a++) { cvc[a] = 0.0; cval[a] = 0.0; lam[a] = 0.0; }
     if (ME > 0 && p > 0) {  // slack start values s0 = d(x0) (optimize.jl:26-28): c_aux with s = 0 gives d(x0) in rows >= m
@@ -561,8 +591,11 @@ struct RegSolver {
   }
 };
 
+#ifndef LFPSQP_REG_MINBLOCKS
+#define LFPSQP_REG_MINBLOCKS 3
+#endif
 template <class Fam, int NPL, int ME, bool INEQ>
-__global__ void __launch_bounds__(128, 3) batched_reg_kernel(const BatchedArgs A) {
+__global__ void __launch_bounds__(128, LFPSQP_REG_MINBLOCKS) batched_reg_kernel(const BatchedArgs A) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
   const int NA = A.n + A.p;

@@ -163,10 +163,11 @@ def test_register_and_shared_memory_kernels_agree(L, monkeypatch):
     monkeypatch.delenv("LFPSQP_BATCHED_KERNEL")
     assert np.array_equal(a[4]["condition"], b[4]["condition"]) and np.array_equal(a[4]["iter"], b[4]["iter"])
     assert np.max(np.linalg.norm(a[0] - b[0], axis=1) / np.linalg.norm(b[0], axis=1)) < 1e-8
-    for k in ("projcg_iters", "retract_outer", "armijo_trials"):
-        frac = (a[5][k] == b[5][k]).mean()
-        print(k, "identical on", frac)
-        assert frac > 0.9   # summation order differs between the two layouts; a few counters move by one
+    for k in ("projcg_negcurv", "retract_outer", "retract_pcg", "armijo_trials", "pp_backtracks", "f_evals"):
+        assert (a[5][k] == b[5][k]).mean() > 0.98, k
+    # projcg's last iterations run at the rounding floor (rg <= 0 / nr < tol on ~1e-16 residuals): its count moves by one
+    # on ~20 % of the instances between ANY two implementations (also oracle vs oracle+fma) without moving the iterates
+    assert np.max(np.abs(a[5]["projcg_iters"] - b[5]["projcg_iters"])) <= 2
     # wider instances exercise the NPL = 1 and NPL = 4 instantiations
     for n2 in (20, 100):
         co = rng.standard_normal((64, n2)); inf2 = np.inf * np.ones(n2)
