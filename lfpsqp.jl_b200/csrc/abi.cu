@@ -5,6 +5,7 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #include "ctx.h"
 #include "batched_tiny.cuh"
@@ -76,7 +77,7 @@ extern "C" int lfpsqp_ctx_create(int device, lfpsqp_ctx **out) {
   }
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
-      cudaMalloc(&c->work_counter, 64) != cudaSuccess) {
+      cudaMalloc(&c->work_counter, 256) != cudaSuccess) {
     g_create_error = "lfpsqp_ctx_create: stream/event creation failed";
     delete c; cudaGetLastError(); return LFPSQP_ERR_CUDA;
   }
@@ -92,6 +93,7 @@ extern "C" void lfpsqp_ctx_destroy(lfpsqp_ctx *c) {
   lfpsqp_comm_destroy(c);
   for (void *b : c->bufs) if (b) cudaFree(b);
   if (c->work_counter) cudaFree(c->work_counter);
+  for (int i = 0; i < 3; i++) if (c->pipe[i]) cudaStreamDestroy(c->pipe[i]);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -254,34 +256,42 @@ int check_common(lfpsqp_ctx *c, int family, int64_t n, int64_t m, int64_t p, int
 
 }  // namespace
 
-extern "C" int lfpsqp_solve_batched_dev(lfpsqp_ctx *c, int family, int64_t n, int64_t m, int64_t p, int64_t B,
-                                        const double *fam_params_dev, int64_t fam_stride, const double *x0_dev,
-                                        const double *xl, const double *xu, const lfpsqp_params *prm, double *x_out_dev,
-                                        double *obj_hist_dev, int64_t H, int64_t *obj_len_dev, double *lambda_dev,
-                                        lfpsqp_term *term_dev, lfpsqp_stats *stats_dev) {
+// argument checks + bound embedding data shared by both batched entry points; fills A except the per-batch pointers
+static int prepare_batched(lfpsqp_ctx *c, int family, int64_t n, int64_t m, int64_t p, int64_t B, const double *xl,
+                           const double *xu, const lfpsqp_params *prm, int64_t H, BatchedArgs &A) {
   int rc = check_common(c, family, n, m, p, B, prm, H);
   if (rc) return rc;
   cudaSetDevice(c->device);
-  c->last_ms = 0; c->last_launches = 0;
-  if (B == 0) return LFPSQP_OK;
-  if (fam_param_count(family, n, m, p) > 0 && !fam_params_dev) return c->fail(LFPSQP_ERR_ARG, "family needs a parameter blob");
   std::vector<double> bnd;
   int ineq = build_bounds(n, p, xl, xu, bnd);
   if (ineq == LFPSQP_ERR_BOUNDS) return c->fail(ineq, "Infeasible: lower bounds cannot be greater than upper bounds");
   if (ineq < 0) return c->fail(ineq, "xl, xu, and x0 must all be the same length (both or neither may be NULL)");
-  BatchedArgs A;
   memset(&A, 0, sizeof(A));
-  A.family = family; A.n = (int)n; A.m = (int)m; A.p = (int)p; A.ineq = ineq; A.B = B;
-  A.fam_params = fam_params_dev; A.fam_stride = fam_stride; A.x0 = x0_dev; A.prm = *prm;
-  A.x_out = x_out_dev; A.obj_hist = obj_hist_dev; A.H = H; A.obj_len = obj_len_dev; A.lambda = lambda_dev;
-  A.term = term_dev; A.stats = stats_dev;
-  if (ineq) {
+  A.family = family; A.n = (int)n; A.m = (int)m; A.p = (int)p; A.ineq = ineq; A.B = B; A.prm = *prm; A.H = H;
+  if (ineq && B > 0) {
     double *dbnd = (double *)c->arena(0, bnd.size() * 8);
     if (!dbnd) return c->fail(LFPSQP_ERR_NOMEM, "device allocation failed");
     cudaMemcpyAsync(dbnd, bnd.data(), bnd.size() * 8, cudaMemcpyHostToDevice, c->stream);
     cudaStreamSynchronize(c->stream);  // bnd is a stack-owned host vector
     A.bnd = dbnd;
   }
+  return LFPSQP_OK;
+}
+
+extern "C" int lfpsqp_solve_batched_dev(lfpsqp_ctx *c, int family, int64_t n, int64_t m, int64_t p, int64_t B,
+                                        const double *fam_params_dev, int64_t fam_stride, const double *x0_dev,
+                                        const double *xl, const double *xu, const lfpsqp_params *prm, double *x_out_dev,
+                                        double *obj_hist_dev, int64_t H, int64_t *obj_len_dev, double *lambda_dev,
+                                        lfpsqp_term *term_dev, lfpsqp_stats *stats_dev) {
+  BatchedArgs A;
+  int rc = prepare_batched(c, family, n, m, p, B, xl, xu, prm, H, A);
+  if (rc) return rc;
+  c->last_ms = 0; c->last_launches = 0;
+  if (B == 0) return LFPSQP_OK;
+  if (fam_param_count(family, n, m, p) > 0 && !fam_params_dev) return c->fail(LFPSQP_ERR_ARG, "family needs a parameter blob");
+  A.fam_params = fam_params_dev; A.fam_stride = fam_stride; A.x0 = x0_dev;
+  A.x_out = x_out_dev; A.obj_hist = obj_hist_dev; A.obj_len = obj_len_dev; A.lambda = lambda_dev;
+  A.term = term_dev; A.stats = stats_dev;
   rc = dispatch_batched(c, A);
   if (rc) return rc;
   cudaError_t e = cudaStreamSynchronize(c->stream);
@@ -291,13 +301,15 @@ extern "C" int lfpsqp_solve_batched_dev(lfpsqp_ctx *c, int family, int64_t n, in
   return LFPSQP_OK;
 }
 
+// Host-buffer entry point.  Large batches are cut into chunks that flow through a 3-stream pipeline
+// (H2D of chunk i+1 and D2H of chunk i-1 overlap the kernel of chunk i; needs pinned host buffers to really overlap).
 extern "C" int lfpsqp_solve_batched(lfpsqp_ctx *c, int family, int64_t n, int64_t m, int64_t p, int64_t B,
                                     const double *fam_params, int64_t fam_stride, const double *x0, const double *xl,
                                     const double *xu, const lfpsqp_params *prm, double *x_out, double *obj_hist,
                                     int64_t H, int64_t *obj_len, double *lambda, lfpsqp_term *term, lfpsqp_stats *stats) {
-  int rc = check_common(c, family, n, m, p, B, prm, H);
+  BatchedArgs A0;
+  int rc = prepare_batched(c, family, n, m, p, B, xl, xu, prm, H, A0);
   if (rc) return rc;
-  cudaSetDevice(c->device);
   if (B == 0) return LFPSQP_OK;
   const int64_t npar = fam_param_count(family, n, m, p);
   if (npar > 0 && !fam_params) return c->fail(LFPSQP_ERR_ARG, "family needs a parameter blob");
@@ -312,20 +324,47 @@ extern "C" int lfpsqp_solve_batched(lfpsqp_ctx *c, int family, int64_t n, int64_
   lfpsqp_stats *d_stats = stats ? (lfpsqp_stats *)c->arena(8, (size_t)B * sizeof(lfpsqp_stats)) : nullptr;
   if (!d_par || !d_x0 || !d_x || !d_obj || !d_lam || !d_len || !d_term || (stats && !d_stats))
     return c->fail(LFPSQP_ERR_NOMEM, "device allocation failed");
-  cudaStream_t s = c->stream;
-  if (par_bytes) cudaMemcpyAsync(d_par, fam_params, par_bytes, cudaMemcpyHostToDevice, s);
-  cudaMemcpyAsync(d_x0, x0, (size_t)n * B * 8, cudaMemcpyHostToDevice, s);
-  cudaMemsetAsync(d_obj, 0xff, (size_t)H * B * 8, s);  // NaN-fill the unused tail of the history
-  rc = lfpsqp_solve_batched_dev(c, family, n, m, p, B, npar ? d_par : nullptr, fam_stride, d_x0, xl, xu, prm, d_x, d_obj, H,
-                                d_len, d_lam, d_term, d_stats);
+  // chunking: keep every chunk big enough to fill the GPU several times over
+  int nchunk = 1;
+  if (B >= 16384) nchunk = (int)std::min<int64_t>(8, B / 8192);
+  const int NS = 3;
+  if (nchunk > 1 && !c->pipe[0]) {
+    for (int i = 0; i < NS; i++) if (cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); nchunk = 1; break; }
+  }
+  cudaStream_t user_stream = c->stream;
+  unsigned long long *counter0 = c->work_counter;
+  if (nchunk > 1) cudaStreamSynchronize(user_stream);   // earlier work on the caller's stream is done before the pipeline starts
+  if (npar && fam_stride == 0) cudaMemcpyAsync(d_par, fam_params, par_bytes, cudaMemcpyHostToDevice, user_stream), cudaStreamSynchronize(user_stream);
+  c->last_launches = 0;
+  int64_t launches = 0;
+  for (int ci = 0; ci < nchunk && rc == 0; ci++) {
+    const int64_t lo = B * ci / nchunk, hi = B * (ci + 1) / nchunk, nb = hi - lo;
+    cudaStream_t s = (nchunk > 1) ? c->pipe[ci % NS] : user_stream;
+    if (npar && fam_stride) cudaMemcpyAsync(d_par + lo * fam_stride, fam_params + lo * fam_stride, (size_t)nb * fam_stride * 8, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_x0 + lo * n, x0 + lo * n, (size_t)n * nb * 8, cudaMemcpyHostToDevice, s);
+    cudaMemsetAsync(d_obj + lo * H, 0xff, (size_t)H * nb * 8, s);  // NaN-fill the unused tail of the history
+    BatchedArgs A = A0;
+    A.B = nb;
+    A.fam_params = npar ? (fam_stride ? d_par + lo * fam_stride : d_par) : nullptr; A.fam_stride = fam_stride;
+    A.x0 = d_x0 + lo * n; A.x_out = d_x + lo * n; A.obj_hist = d_obj + lo * H; A.obj_len = d_len + lo;
+    A.lambda = d_lam + lo * ME; A.term = d_term + lo; A.stats = d_stats ? d_stats + lo : nullptr;
+    c->stream = s; c->work_counter = counter0 + (ci % 8);
+    rc = dispatch_batched(c, A);
+    launches += c->last_launches;
+    if (rc) break;
+    cudaMemcpyAsync(x_out + lo * n, d_x + lo * n, (size_t)n * nb * 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(obj_hist + lo * H, d_obj + lo * H, (size_t)H * nb * 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(obj_len + lo, d_len + lo, (size_t)nb * 8, cudaMemcpyDeviceToHost, s);
+    if (ME) cudaMemcpyAsync(lambda + lo * ME, d_lam + lo * ME, (size_t)ME * nb * 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(term + lo, d_term + lo, (size_t)nb * sizeof(lfpsqp_term), cudaMemcpyDeviceToHost, s);
+    if (stats) cudaMemcpyAsync(stats + lo, d_stats + lo, (size_t)nb * sizeof(lfpsqp_stats), cudaMemcpyDeviceToHost, s);
+  }
+  c->stream = user_stream; c->work_counter = counter0;
+  c->last_launches = launches;
+  cudaError_t e = cudaSuccess;
+  if (nchunk > 1) { for (int i = 0; i < NS; i++) { cudaError_t ei = cudaStreamSynchronize(c->pipe[i]); if (ei != cudaSuccess) e = ei; } }
+  else e = cudaStreamSynchronize(user_stream);
   if (rc) return rc;
-  cudaMemcpyAsync(x_out, d_x, (size_t)n * B * 8, cudaMemcpyDeviceToHost, s);
-  cudaMemcpyAsync(obj_hist, d_obj, (size_t)H * B * 8, cudaMemcpyDeviceToHost, s);
-  cudaMemcpyAsync(obj_len, d_len, (size_t)B * 8, cudaMemcpyDeviceToHost, s);
-  if (ME) cudaMemcpyAsync(lambda, d_lam, (size_t)ME * B * 8, cudaMemcpyDeviceToHost, s);
-  cudaMemcpyAsync(term, d_term, (size_t)B * sizeof(lfpsqp_term), cudaMemcpyDeviceToHost, s);
-  if (stats) cudaMemcpyAsync(stats, d_stats, (size_t)B * sizeof(lfpsqp_stats), cudaMemcpyDeviceToHost, s);
-  cudaError_t e = cudaStreamSynchronize(s);
-  if (e != cudaSuccess) return c->cuda_fail(e, "batched solve (copy back)");
+  if (e != cudaSuccess) return c->cuda_fail(e, "batched solve (pipeline)");
   return LFPSQP_OK;
 }

@@ -16,7 +16,7 @@ struct CommState {           // NCCL communicator of a column-sharded solve (com
 
 struct lfpsqp_ctx {
   int device = 0, sm_count = 148, smem_optin = 232448;
-  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaStream_t own_stream = nullptr, stream = nullptr, pipe[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   unsigned long long *work_counter = nullptr;
   double last_ms = 0.0;
