@@ -146,6 +146,28 @@ int lfpsqp_large_project(lfpsqp_ctx *ctx, const double *v_loc, double *v_out_loc
 int lfpsqp_large_projcg(lfpsqp_ctx *ctx, const double *x_loc, const double *lam, double tol, int64_t maxit, int chunk,
                         double *sol_out_loc, int64_t *iters, double *nr, int *status, double *ms);
 
+/*   retract : retract!(cval, xnew, c!, xtilde, x, method) (src/retractions.jl:75-177 NR [method 0] / :265-441 ProjPenalty
+ *             [method 1]) with the factorisation at x_base, as armijo! calls it (src/linesearch.jl:52); flag as the reference
+ *   pcg     : pcg!(mu, J, no_precondition, x=0, r=b, ...) (src/retractions.jl:179-246) with J = jac(x_point) */
+int lfpsqp_large_retract(lfpsqp_ctx *ctx, int method, const double *x_base_loc, const double *xtilde_loc,
+                         const lfpsqp_params *params, double *xnew_out_loc, double *cval_out, int *flag, int64_t *iters,
+                         int64_t *pcg_iters);
+int lfpsqp_large_pcg(lfpsqp_ctx *ctx, const double *x_point_loc, double mu, const double *b_loc, double tol, int64_t maxiter,
+                     double *x_out_loc, double *r_out_loc, int *flag, int64_t *iters);
+
+/* Unit-level bound embedding (src/inequality_helper.jl; y_retract! src/retractions.jl:451-500) on one instance; runs the
+ * device code of the batched solver.  J: m x n row-major (== Jct column-major), may be NULL when m = 0.
+ *  op 0 generate_initial_y! (:92-109)   in x (n)                          out xaug (2n)
+ *  op 1 calculate_h! (:112-122)         in xaug (2n)                      out h (n)
+ *  op 2 inequality_gradient! (:125-141) in xaug                           out [Dx | Dy | S] (3n)
+ *  op 3 y_retract!                      in [xaug_base | xaug_trial] (4n)  out retracted trial (2n)
+ *  op 4 bigA * v (:215-231)             in [xaug | v (n+m)]               out 2n
+ *  op 5 bigA' * w (:254-271)            in [xaug | w (2n)]                out n+m
+ *  op 6 d - Q Q'd, lambda, lambda_y (optimize.jl:316-317,:332; calculate_lambda_kkt! :286-308)
+ *                                       in [xaug | d (2n)]                out [d_proj (2n) | lambda (m) | lambda_y (n)] */
+int lfpsqp_ineq_op(lfpsqp_ctx *ctx, int op, int64_t n, int64_t m, const double *xl, const double *xu, const double *J,
+                   const double *in, int64_t in_len, double *out, int64_t out_len);
+
 /* Communicator of the column-sharded large-n mode: one process per GPU, NCCL (bound with dlopen so the process shares
  * the libnccl.so.2 that e.g. torch.distributed loaded; nccl_lib_path may be NULL).  Rank 0 creates the 128-byte unique
  * id, the host program broadcasts it (any transport), every rank calls lfpsqp_comm_init BEFORE lfpsqp_large_setup. */

@@ -31,7 +31,8 @@ EXPORTS = [
     "lfpsqp_ctx_set_stream", "lfpsqp_last_kernel_ms", "lfpsqp_last_launches", "lfpsqp_solve_batched",
     "lfpsqp_solve_batched_dev", "lfpsqp_bench_fp64_peak", "lfpsqp_solve_large", "lfpsqp_large_setup",
     "lfpsqp_large_solve", "lfpsqp_large_factor", "lfpsqp_large_project", "lfpsqp_large_projcg",
-    "lfpsqp_comm_unique_id", "lfpsqp_comm_init", "lfpsqp_comm_destroy",
+    "lfpsqp_comm_unique_id", "lfpsqp_comm_init", "lfpsqp_comm_destroy", "lfpsqp_large_retract", "lfpsqp_large_pcg",
+    "lfpsqp_ineq_op",
 ]
 
 _lib = None
@@ -70,6 +71,9 @@ def load():
         lib.lfpsqp_comm_unique_id.argtypes = [P, C.c_char_p]
         lib.lfpsqp_comm_init.argtypes = [P, C.c_int, C.c_int, P, C.c_char_p]
         lib.lfpsqp_comm_destroy.argtypes = [P]
+        lib.lfpsqp_large_retract.argtypes = [P, C.c_int, P, P, P, P, P, P, P, P]
+        lib.lfpsqp_large_pcg.argtypes = [P, P, C.c_double, P, C.c_double, I, P, P, P, P]
+        lib.lfpsqp_ineq_op.argtypes = [P, C.c_int, I, I, P, P, P, P, I, P, I]
         _lib = lib
     return _lib
 

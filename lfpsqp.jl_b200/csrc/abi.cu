@@ -256,6 +256,8 @@ int check_common(lfpsqp_ctx *c, int family, int64_t n, int64_t m, int64_t p, int
 
 }  // namespace
 
+int build_bounds_public(int64_t n, int64_t p, const double *xl, const double *xu, std::vector<double> &bnd) { return build_bounds(n, p, xl, xu, bnd); }
+
 // argument checks + bound embedding data shared by both batched entry points; fills A except the per-batch pointers
 static int prepare_batched(lfpsqp_ctx *c, int family, int64_t n, int64_t m, int64_t p, int64_t B, const double *xl,
                            const double *xu, const lfpsqp_params *prm, int64_t H, BatchedArgs &A) {

@@ -231,7 +231,7 @@ static void project(LargeState &S, double *v, double *lam_out, int pred, int wan
     double s = 0.0;
     for (int k = 0; k < ns; k++) s += cp[(int64_t)k * n + j];
     double r = v[j] - s; v[j] = r;
-    acc[0] += r * r; acc[3] = fmax(acc[3], fabs(r));
+    acc[0] += r * r; acc[3] = nanmax(acc[3], fabs(r));
   }, 0, want_norms ? 1 : 0, want_norms);
   S.launches++;
 }
@@ -286,6 +286,33 @@ static int projcg(lfpsqp_ctx *c, LargeState &S, double tol, int64_t maxit, int c
   return 0;
 }
 
+// ------------------------------------------------------------------ pcg! (retractions.jl:179-246), M! = copy, on (J'J + mu I) dx = r
+// state: dx = S.w3 (initial guess), r = S.w0 (= b - A dx), p = S.w1 (zeroed by the caller), z = S.w2;
+// r.r partials of the start residual in loop slot 5.  Device-predicated, enqueued in chunks.
+static int run_pcg(lfpsqp_ctx *c, LargeState &S, double mu, double tol, int64_t maxiter) {
+  const int64_t n = S.n_loc; const int m = S.m;
+  double *r = S.w0, *pv = S.w1, *z = S.w2, *dx = S.w3;
+  S.hctrl->tol = tol; S.hctrl->mu = mu; S.hctrl->pcg_iter = 0; S.hctrl->pcg_lim = (int)std::min<int64_t>(maxiter, 2000000000); S.hctrl->pcg_status = 0;
+  write_ctrl_fields(S);
+  int64_t k = 0;
+  while (S.hctrl->pcg_status == 0) {
+    for (int q = 0; q < S.pcg_chunk; q++, k++) {
+      const int par = (int)(k & 1);
+      if (S.world > 1) comm_allreduce_loop_slot(S, 5 + par, S.np_loop_raw);
+      pcg_a_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, pv, r, S.lp, S.np_loop, par, k == 0, S.ctrl);
+      rows_dot(S, S.J, S.ldj, m, n, pv, S.tm, 2);
+      if (S.world > 1) comm_allreduce(S, S.tm, m);
+      cols_dot(S, S.J, S.ldj, m, n, S.tm, 2);
+      pcg_z_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, z, pv, S.cpart, S.nsplit, S.lp, S.ctrl);
+      if (S.world > 1) comm_allreduce_loop_slot(S, 4, S.np_loop_raw);
+      pcg_x_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, dx, r, pv, z, S.lp, S.np_loop, par, S.ctrl);
+      S.launches += 3;
+    }
+    if (read_ctrl(c, S)) return -1;
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------ retract!(::ProjPenalty) (retractions.jl:265-441) + pcg! (:179-246)
 // xtil -> xnew ; returns flag, it1 (outer), it2 (pcg total)
 static int retract_pp(lfpsqp_ctx *c, LargeState &S, int *flag_out, int *it1, int *it2) {
@@ -300,7 +327,7 @@ static int retract_pp(lfpsqp_ctx *c, LargeState &S, int *flag_out, int *it1, int
   while (i < prm.maxiter_retract) {
     fam_c_jac(S, S.J, cval, xnew);                                                       // :340
     // curtol = |c|_inf (slot 3 max), c.c (slot 0) ; g = xnew - xtilde, g.g (slot 1)
-    vec(S, m, [=] __device__(int64_t a, double *acc) { double v = cval[a]; acc[0] += v * v; acc[3] = fmax(acc[3], fabs(v)); }, 0, 1, 1);
+    vec(S, m, [=] __device__(int64_t a, double *acc) { double v = cval[a]; acc[0] += v * v; acc[3] = nanmax(acc[3], fabs(v)); }, 0, 1, 1);
     finalize(S, 1u, 8u, 1u | 8u);
     if (read_ctrl(c, S)) return -1;
     double curtol = S.hctrl->s[3], cc = S.hctrl->s[0];
@@ -316,25 +343,7 @@ static int retract_pp(lfpsqp_ctx *c, LargeState &S, int *flag_out, int *it1, int
     }
     if (read_ctrl(c, S)) return -1;
     double prev_obj = cc + mu * S.hctrl->s[1];                                           // :366
-    // pcg! with tol = eps_c, maxiter_pcg
-    S.hctrl->tol = prm.eps_c; S.hctrl->mu = mu; S.hctrl->pcg_iter = 0; S.hctrl->pcg_lim = (int)prm.maxiter_pcg; S.hctrl->pcg_status = 0;
-    write_ctrl_fields(S);
-    int64_t k = 0;
-    while (S.hctrl->pcg_status == 0) {
-      for (int q = 0; q < S.pcg_chunk; q++, k++) {
-        const int par = (int)(k & 1);
-        if (S.world > 1) comm_allreduce_loop_slot(S, 5 + par, S.np_loop_raw);
-        pcg_a_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, pv, r, S.lp, S.np_loop, par, k == 0, S.ctrl);
-        rows_dot(S, S.J, S.ldj, m, n, pv, S.tm, 2);
-        if (S.world > 1) comm_allreduce(S, S.tm, m);
-        cols_dot(S, S.J, S.ldj, m, n, S.tm, 2);
-        pcg_z_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, z, pv, S.cpart, S.nsplit, S.lp, S.ctrl);
-        if (S.world > 1) comm_allreduce_loop_slot(S, 4, S.np_loop_raw);
-        pcg_x_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, dx, r, pv, z, S.lp, S.np_loop, par, S.ctrl);
-        S.launches += 3;
-      }
-      if (read_ctrl(c, S)) return -1;
-    }
+    if (run_pcg(c, S, mu, prm.eps_c, prm.maxiter_pcg)) return -1;                       // :375
     int pcg_i = S.hctrl->pcg_iter;
     pcg_total += pcg_i;
     if (pcg_i == prm.maxiter_pcg) { flag = 2; break; }                                   // :240-243, :377-381
@@ -385,7 +394,7 @@ static int retract_nr(lfpsqp_ctx *c, LargeState &S, int *flag_out, int *it1) {
   cudaMemcpyAsync(D, S.Linv, (size_t)m * ldm * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);   // D0 = L^-1
   int i = 0;
   while (i < S.prm.maxiter_retract) {
-    vec(S, m, [=] __device__(int64_t a, double *acc) { acc[3] = fmax(acc[3], fabs(cval[a])); }, 0, 0, 1);
+    vec(S, m, [=] __device__(int64_t a, double *acc) { acc[3] = nanmax(acc[3], fabs(cval[a])); }, 0, 0, 1);
     finalize(S, 0, 8u, 8u);
     if (read_ctrl(c, S)) return -1;
     if (S.hctrl->s[3] < S.prm.eps_c) break;                                              // :135
@@ -452,7 +461,7 @@ static int solve(lfpsqp_ctx *c, LargeState &S, const double *x0_host, double *x_
       if (factorize(c, S)) return LFPSQP_ERR_CUDA;
       project(S, d, S.lam, 0, 1);                                                       // :306-307, :333-343
     } else {
-      vec(S, n, [=] __device__(int64_t i, double *acc) { double r = d[i]; acc[0] += r * r; acc[3] = fmax(acc[3], fabs(r)); }, 0, 1, 1);
+      vec(S, n, [=] __device__(int64_t i, double *acc) { double r = d[i]; acc[0] += r * r; acc[3] = nanmax(acc[3], fabs(r)); }, 0, 1, 1);
     }
     finalize(S, 1u, 8u);
     if (read_ctrl(c, S)) return LFPSQP_ERR_CUDA;
@@ -740,5 +749,58 @@ extern "C" int lfpsqp_large_projcg(lfpsqp_ctx *c, const double *x_loc, const dou
   if (nr) *nr = S.hctrl->nr;
   if (status) *status = S.hctrl->status;
   c->last_ms = t; c->last_launches = S.launches;
+  return LFPSQP_OK;
+}
+
+// Unit-level: retract!(cval, xnew, c!, xtilde, x, method) (src/retractions.jl:75-177 NR / :265-441 ProjPenalty) with the
+// factorisation taken at x_base (as armijo! calls it, linesearch.jl:52).  method: 0 = NR, 1 = ProjPenalty.
+extern "C" int lfpsqp_large_retract(lfpsqp_ctx *c, int method, const double *x_base_loc, const double *xtilde_loc,
+                                    const lfpsqp_params *prm, double *xnew_out_loc, double *cval_out, int *flag,
+                                    int64_t *iters, int64_t *pcg_iters) {
+  int rc = need_large(c); if (rc) return rc;
+  LargeState &S = *c->large;
+  lfpsqp_params p2 = *prm; p2.do_project_retract = (method == 0) ? 0 : 1;
+  rc = prep_params(c, S, &p2); if (rc) return rc;
+  if (S.m < 1) return c->fail(LFPSQP_ERR_ARG, "retraction needs m > 0");
+  const int64_t n = S.n_loc;
+  CK(cudaMemcpyAsync(S.x, x_base_loc, n * 8, cudaMemcpyHostToDevice, S.stream));
+  CK(cudaMemcpyAsync(S.xtil, xtilde_loc, n * 8, cudaMemcpyHostToDevice, S.stream));
+  memset(S.hctrl, 0, sizeof(LargeCtrl)); write_ctrl_fields(S);
+  S.reset_counters();
+  fam_c_jac(S, S.J, S.cval, S.x);
+  if (factorize(c, S)) return LFPSQP_ERR_CUDA;
+  int fl = 0, i1 = 0, i2 = 0;
+  if (method == 0) { if (retract_nr(c, S, &fl, &i1)) return LFPSQP_ERR_CUDA; }
+  else { if (retract_pp(c, S, &fl, &i1, &i2)) return LFPSQP_ERR_CUDA; }
+  CK(cudaMemcpyAsync(xnew_out_loc, S.xnew, n * 8, cudaMemcpyDeviceToHost, S.stream));
+  if (cval_out) CK(cudaMemcpyAsync(cval_out, S.cval, S.m * 8, cudaMemcpyDeviceToHost, S.stream));
+  CK(cudaStreamSynchronize(S.stream));
+  if (flag) *flag = fl; if (iters) *iters = i1; if (pcg_iters) *pcg_iters = i2;
+  c->last_launches = S.launches;
+  return LFPSQP_OK;
+}
+
+// Unit-level: pcg!(mu, J, no_precondition, x, r, p, z, tmp_m, tol, maxiter) (src/retractions.jl:179-246) with J = jac(x_point),
+// x = 0, r = b.  Outputs the solution, the final residual, flag (1 iff iters == maxiter) and the iteration count.
+extern "C" int lfpsqp_large_pcg(lfpsqp_ctx *c, const double *x_point_loc, double mu, const double *b_loc, double tol,
+                                int64_t maxiter, double *x_out_loc, double *r_out_loc, int *flag, int64_t *iters) {
+  int rc = need_large(c); if (rc) return rc;
+  LargeState &S = *c->large;
+  if (S.m < 1) return c->fail(LFPSQP_ERR_ARG, "pcg needs m > 0");
+  const int64_t n = S.n_loc;
+  double *r = S.w0, *pv = S.w1, *dx = S.w3, *lp = S.lp;
+  CK(cudaMemcpyAsync(S.x, x_point_loc, n * 8, cudaMemcpyHostToDevice, S.stream));
+  CK(cudaMemcpyAsync(r, b_loc, n * 8, cudaMemcpyHostToDevice, S.stream));
+  memset(S.hctrl, 0, sizeof(LargeCtrl)); write_ctrl_fields(S);
+  S.reset_counters();
+  fam_c_jac(S, S.J, S.cval, S.x);
+  pcg_start_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, r, dx, pv, lp);
+  if (run_pcg(c, S, mu, tol, maxiter)) return LFPSQP_ERR_CUDA;
+  if (x_out_loc) CK(cudaMemcpyAsync(x_out_loc, dx, n * 8, cudaMemcpyDeviceToHost, S.stream));
+  if (r_out_loc) CK(cudaMemcpyAsync(r_out_loc, r, n * 8, cudaMemcpyDeviceToHost, S.stream));
+  CK(cudaStreamSynchronize(S.stream));
+  if (iters) *iters = S.hctrl->pcg_iter;
+  if (flag) *flag = (S.hctrl->pcg_iter == maxiter) ? 1 : 0;
+  c->last_launches = S.launches;
   return LFPSQP_OK;
 }

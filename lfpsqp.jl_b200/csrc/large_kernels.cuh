@@ -19,6 +19,10 @@
 
 namespace lfpsqp {
 
+// NaN-propagating max (Julia's norm(x, Inf) returns NaN if any entry is NaN; fmax would drop it and a diverged
+// retraction would look converged)
+__device__ __forceinline__ double nanmax(double a, double b) { return (b > a || isnan(b)) ? b : a; }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -307,6 +311,18 @@ __global__ void __launch_bounds__(256) pp_rhs_kernel(int64_t n, double *__restri
     for (int k = 0; k < nsplit; k++) s += cpart[(int64_t)k * n + i];
     double gi = s + mu * g[i];
     g[i] = gi; dx[i] = 0.0; r[i] = gi; p[i] = 0.0; a += gi * gi;
+  }
+  a = block_sum(a, sh);
+  if (threadIdx.x == 0) lp[5 * MAXP + blockIdx.x] = a;
+}
+
+// pcg! start state for the unit-level export: x = 0, p = 0, r.r partials -> slot 5
+__global__ void __launch_bounds__(256) pcg_start_kernel(int64_t n, const double *__restrict__ r, double *__restrict__ dx,
+                                                        double *__restrict__ p, double *lp) {
+  __shared__ double sh[33];
+  double a = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    dx[i] = 0.0; p[i] = 0.0; double ri = r[i]; a += ri * ri;
   }
   a = block_sum(a, sh);
   if (threadIdx.x == 0) lp[5 * MAXP + blockIdx.x] = a;

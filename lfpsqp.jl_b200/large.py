@@ -57,6 +57,26 @@ class LargeProblem:
         self.ctx.check(self.ctx.lib.lfpsqp_large_project(self.ctx.h, _lib.ptr(v), _lib.ptr(out), _lib.ptr(lam)))
         return out, lam[:self.m]
 
+    def retract(self, method, x_base, xtilde, param=None):
+        """retract! with method "nr" | "pp" -> (flag, xnew, cval, iters, pcg_iters)"""
+        cp = (param or LFPSQPParams()).to_c()
+        xb = np.ascontiguousarray(x_base, dtype=np.float64); xt = np.ascontiguousarray(xtilde, dtype=np.float64)
+        xnew = np.empty(self.n_loc); cval = np.zeros(max(self.m, 1))
+        fl = C.c_int(0); it = C.c_int64(0); pit = C.c_int64(0)
+        self.ctx.check(self.ctx.lib.lfpsqp_large_retract(self.ctx.h, 0 if method == "nr" else 1, _lib.ptr(xb), _lib.ptr(xt),
+                                                         C.cast(C.pointer(cp), C.c_void_p), _lib.ptr(xnew), _lib.ptr(cval),
+                                                         C.cast(C.pointer(fl), C.c_void_p), C.cast(C.pointer(it), C.c_void_p),
+                                                         C.cast(C.pointer(pit), C.c_void_p)))
+        return fl.value, xnew, cval[:self.m], it.value, pit.value
+
+    def pcg(self, x_point, mu, b, tol=1e-6, maxiter=100):
+        """pcg! on (J'J + mu I) x = b with J = jac(x_point) -> (x, r, flag, iters)"""
+        xp = np.ascontiguousarray(x_point, dtype=np.float64); b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty(self.n_loc); r = np.empty(self.n_loc); fl = C.c_int(0); it = C.c_int64(0)
+        self.ctx.check(self.ctx.lib.lfpsqp_large_pcg(self.ctx.h, _lib.ptr(xp), mu, _lib.ptr(b), tol, maxiter, _lib.ptr(x), _lib.ptr(r),
+                                                     C.cast(C.pointer(fl), C.c_void_p), C.cast(C.pointer(it), C.c_void_p)))
+        return x, r, fl.value, it.value
+
     def projcg(self, x, lam=None, tol=0.0, maxit=10, chunk=0, want_solution=True):
         x = np.ascontiguousarray(x, dtype=np.float64)
         lam = None if lam is None else np.ascontiguousarray(lam, dtype=np.float64)
@@ -66,6 +86,22 @@ class LargeProblem:
                                                         C.cast(C.pointer(it), C.c_void_p), C.cast(C.pointer(nr), C.c_void_p),
                                                         C.cast(C.pointer(st), C.c_void_p), C.cast(C.pointer(ms), C.c_void_p)))
         return dict(sol=sol, iters=it.value, nr=nr.value, status=st.value, ms=ms.value)
+
+
+def ineq_op(op, xl, xu, inp, J=None, ctx=None):
+    """Unit-level bound-embedding ops on the device (lfpsqp_ineq_op): op in {"initial_y", "h", "gradient", "y_retract",
+    "bigA", "bigAt", "project"}.  J: (m, n) row-major (= Jct', src/optimize.jl:190)."""
+    ctx = ctx or _lib.default_context()
+    code = dict(initial_y=0, h=1, gradient=2, y_retract=3, bigA=4, bigAt=5, project=6)[op]
+    xl = np.ascontiguousarray(xl, dtype=np.float64); xu = np.ascontiguousarray(xu, dtype=np.float64)
+    n = len(xl); m = 0 if J is None else J.shape[0]
+    Jc = None if J is None else np.ascontiguousarray(J, dtype=np.float64)
+    inp = np.ascontiguousarray(inp, dtype=np.float64)
+    olen = [2 * n, n, 3 * n, 2 * n, 2 * n, n + m, 3 * n + m][code]
+    out = np.zeros(olen)
+    ctx.check(ctx.lib.lfpsqp_ineq_op(ctx.h, code, n, m, _lib.ptr(xl), _lib.ptr(xu), _lib.ptr(Jc), _lib.ptr(inp), inp.size,
+                                     _lib.ptr(out), olen))
+    return out
 
 
 def make_diagquad(n, m, seed=0, cond=1e4, dtype=np.float64):

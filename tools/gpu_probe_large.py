@@ -84,3 +84,25 @@ if "c5" in which:
     x, obj, lamk, info, st, status = P.solve(x0h, L.LFPSQPParams(), return_stats=True)
     t1 = time.time()
     print("C5 full solve:", info, "status", status, "%.2f s" % (t1 - t0), st, "f:", obj[:3], obj[-1], "launches", ctx.last_launches, flush=True)
+
+if "c4" in which:
+    npts = 4096
+    n, m = 3 * npts, npts
+    rng = np.random.Generator(np.random.Philox(key=4))
+    x0 = rng.standard_normal((npts, 3)); x0 /= np.linalg.norm(x0, axis=1, keepdims=True); x0 = x0.ravel()
+    P = L.LargeProblem(L.families.thomson(npts), ctx)
+    for rep in range(2):
+        t0 = time.time(); fac = P.factor(x0, want=()); t1 = time.time()
+        print("C4 factor: gram %.3f ms (%.2f TFLOP/s), total factor wall %.1f ms rankdef %d" % (
+            fac["gram_ms"], m * (m + 1.0) * n / fac["gram_ms"] / 1e9, (t1 - t0) * 1e3, fac["rank_deficient"]), flush=True)
+    lam0 = np.full(m, 50.0)   # positive multipliers keep the projected Hessian positive: no negative-curvature exit
+    for chunk in (4, 16):
+        r = P.projcg(x0, lam=lam0, tol=0.0, maxit=48, chunk=chunk, want_solution=False)
+        per = r["ms"] / max(r["iters"], 1)
+        bytes_it = 16.0 * m * n + 8.0 * m * m + 104.0 * n
+        print("C4 projcg chunk=%d: %d iters status %d %.3f ms/iter -> %.1f it/s, %.1f GB/s (%.1f%% of 6543)" % (
+            chunk, r["iters"], r["status"], per, 1e3 / per, bytes_it / per / 1e6, bytes_it / per / 1e6 / 65.434), flush=True)
+    t0 = time.time()
+    x, obj, lamk, info, st, status = P.solve(x0, L.LFPSQPParams(maxiter=20), return_stats=True)
+    t1 = time.time()
+    print("C4 20 outer iterations:", info, "status", status, "%.2f s" % (t1 - t0), st, "f:", obj[:2], obj[-1], "launches", ctx.last_launches, flush=True)
