@@ -168,7 +168,7 @@ int build_bounds(int64_t n, int64_t p, const double *xl, const double *xu, std::
 
 template <class Fam>
 int launch_warp(lfpsqp_ctx *c, BatchedArgs &A, int use_nr) {
-  WarpLayout L(A.n, A.m, A.p, A.ineq, use_nr);
+  WarpLayout L(A.n, A.m, A.p, A.ineq, use_nr, (A.prm.linesearch != 0 && !A.prm.disable_linesearch) ? 1 : 0);
   const size_t bnd_bytes = (size_t)(((A.ineq ? 5 * L.NA : 0) + 1) & ~1) * 8;
   const size_t per_warp = (size_t)L.total * 8;
   const size_t cap = (size_t)c->smem_optin;
@@ -227,7 +227,7 @@ int dispatch_batched(lfpsqp_ctx *c, BatchedArgs &A) {
   }
   switch (A.family) {
     case LFPSQP_FAM_ROSENBROCK:
-      if (!A.ineq) return launch_tiny<FamRosenbrock, 2>(c, A);
+      if (!A.ineq && !(A.prm.linesearch != 0 && !A.prm.disable_linesearch)) return launch_tiny<FamRosenbrock, 2>(c, A);
       return launch_warp<FamRosenbrock>(c, A, use_nr);
     case LFPSQP_FAM_README_EQ: return launch_warp<FamReadmeEq>(c, A, use_nr);
     case LFPSQP_FAM_README_INEQ: return launch_warp<FamReadmeIneq>(c, A, use_nr);
@@ -249,8 +249,6 @@ int check_common(lfpsqp_ctx *c, int family, int64_t n, int64_t m, int64_t p, int
   if (!fam_valid(family, n, m, p)) return c->fail(LFPSQP_ERR_FAMILY, "family %d does not support n=%lld m=%lld p=%lld", family,
                                                   (long long)n, (long long)m, (long long)p);
   if (prm->beta > 0) return c->fail(LFPSQP_ERR_UNSUPPORTED, "beta>0 (stochastic perturbation, optimize.jl:264-273) needs Julia's RNG stream");
-  if (prm->linesearch != 0 && !prm->disable_linesearch)
-    return c->fail(LFPSQP_ERR_UNSUPPORTED, "linesearch=exact (linesearch.jl:107-339) is not on the device path yet");
   return LFPSQP_OK;
 }
 

@@ -36,6 +36,7 @@ int launch(lfpsqp_ctx *c, BatchedArgs &A) {
 int launch_batched_reg(lfpsqp_ctx *c, BatchedArgs &A) {
   const char *force = getenv("LFPSQP_BATCHED_KERNEL");
   if (force && strcmp(force, "smem") == 0) return 1;
+  if (A.prm.linesearch != 0 && !A.prm.disable_linesearch) return 1;   // exact_linesearch! lives in the shared-memory solver
   const int NA = A.n + A.p, ME = A.m + A.p;
   switch (A.family) {
     case LFPSQP_FAM_README_INEQ:

@@ -20,11 +20,12 @@ namespace lfpsqp {
 
 // Per-instance shared-memory layout (in doubles).  Host and device compute the same offsets.
 struct WarpLayout {
-  int n, m, p, NA, ME, N, M, ineq, use_nr;
+  int n, m, p, NA, ME, N, M, ineq, use_nr, use_exact;
+  int o_ex[4];
   int o_x, o_xnew, o_xtil, o_g, o_d, o_nd, o_w[5], o_J, o_G, o_cval, o_lam, o_tm, o_cvaug, o_u, o_scr, o_Dx, o_Dy, o_S,
       o_lamy, o_D, o_nr, total;
-  __host__ __device__ WarpLayout(int n_, int m_, int p_, int ineq_, int use_nr_) {
-    n = n_; m = m_; p = p_; ineq = ineq_; use_nr = use_nr_;
+  __host__ __device__ WarpLayout(int n_, int m_, int p_, int ineq_, int use_nr_, int use_exact_ = 0) {
+    n = n_; m = m_; p = p_; ineq = ineq_; use_nr = use_nr_; use_exact = use_exact_;
     NA = n + p; ME = m + p; N = ineq ? 2 * NA : NA; M = ineq ? ME + NA : ME;
     int o = 0;
     auto take = [&](int k) { int r = o; o += k; return r; };
@@ -35,6 +36,7 @@ struct WarpLayout {
     if (ineq) { o_Dx = take(NA); o_Dy = take(NA); o_S = take(NA); o_lamy = take(NA); }
     else { o_Dx = o_Dy = o_S = o_lamy = 0; }
     if (use_nr && ME > 0) { o_D = take(ME * ME); o_nr = take(3 * ME); } else { o_D = o_nr = 0; }
+    for (int i = 0; i < 4; i++) o_ex[i] = use_exact ? take(N) : 0;
     total = (o + 1) & ~1;
   }
 };
@@ -542,6 +544,80 @@ struct Solver {
     return flag;
   }
 
+  // ------------------------------------------------------------ exact_linesearch! (linesearch.jl:107-339)
+  // golden-section search with bracketing; every trial point is retracted.  Four rotating point buffers.
+  LFPSQP_DEV int exact_linesearch(int kind, double fval, double *newf_o, double *f_diff_o, double *step_diff_o) {
+    const double phi1 = (3.0 - sqrt(5.0)) / 2.0, phi2 = (sqrt(5.0) - 1.0) / 2.0, phi3 = (sqrt(5.0) + 1.0) / 2.0;
+    double Delta = prm.alpha;
+    double f_a = 0, f_b = 0, f_c = 0, f_d = 0, a_a = 0, a_b = 0, a_c = 0, a_d = 0;
+    double *x_a = sm + L.o_ex[0], *x_b = sm + L.o_ex[1], *x_c = sm + L.o_ex[2], *x_d = sm + L.o_ex[3], *swp;
+    bool do_shrinking = true;
+    int flag = 0, i1, i2;
+    // trial point pt = x + al*d, retracted in place
+    auto TRIAL = [&](double *pt, double al) {
+      for (int k = g.lane; k < N; k += G::SIZE) xtil[k] = x[k] + al * d[k];
+      g.sync();
+      flag = retract(kind, &i1, &i2);
+      st.armijo_trials++;
+      copy(pt, xnew, N);
+    };
+    copy(x_d, x, N); f_d = fval;
+    while (true) {                                             // growing (:150-189)
+      swp = x_b; x_b = x_c; x_c = x_d; x_d = swp;
+      f_b = f_c; f_c = f_d; a_b = a_c; a_c = a_d;
+      TRIAL(x_d, a_d + Delta);
+      a_d += Delta;
+      if (flag > 0 || a_d > 1.0) { f_d = INFINITY; break; }
+      f_d = f_aux(x_d);
+      if (f_d > f_c) break;
+      do_shrinking = false;
+      Delta *= phi3;
+    }
+    if (do_shrinking) {                                        // (:192-239)
+      f_b = fval; a_b = 0.0; copy(x_b, x, N);
+      f_c = INFINITY; a_c = Delta;
+      swp = x_d; x_d = x_c; x_c = swp;
+      while (true) {
+        swp = x_d; x_d = x_c; x_c = swp;
+        f_d = f_c; a_d = a_c;
+        TRIAL(x_c, phi1 * a_c);
+        a_c *= phi1;
+        if (flag > 0 || a_c > 1.0) f_c = INFINITY; else f_c = f_aux(x_c);
+        if (f_c <= fval || a_c < 1e-100) break;
+      }
+    }
+    f_a = f_b; f_b = f_c; a_a = a_b; a_b = a_c;                // (:242-266)
+    swp = x_a; x_a = x_b; x_b = x_c; x_c = swp;
+    a_c = a_a + phi2 * (a_d - a_a);
+    TRIAL(x_c, a_c);
+    if (flag > 0 || a_c > 1.0) f_c = INFINITY; else f_c = f_aux(x_c);
+    const double nd_ = sqrt(dot(d, d, N));
+    while ((a_c - a_b) > 1e-6 * nd_) {                         // golden-section main loop (:270-322)
+      if (f_b < f_c || isinf(f_c)) {
+        swp = x_d; x_d = x_c; x_c = x_b; x_b = swp;
+        f_d = f_c; f_c = f_b; a_d = a_c; a_c = a_b;
+        a_b = a_a + phi1 * (a_d - a_a);
+        TRIAL(x_b, a_b);
+        f_b = f_aux(x_b);
+      } else {
+        swp = x_a; x_a = x_b; x_b = x_c; x_c = swp;
+        f_a = f_b; f_b = f_c; a_a = a_b; a_b = a_c;
+        a_c = a_a + phi2 * (a_d - a_a);
+        TRIAL(x_c, a_c);
+        if (flag > 0 || a_c > 1.0) f_c = INFINITY; else f_c = f_aux(x_c);
+      }
+    }
+    (void)f_a; (void)f_d;
+    double newf;
+    if (f_b < f_c) { copy(xnew, x_b, N); newf = f_b; } else { copy(xnew, x_c, N); newf = f_c; }   // (:325-333)
+    double s = 0;
+    for (int k = g.lane; k < NA; k += G::SIZE) { double t = xnew[k] - x[k]; s += t * t; }
+    *step_diff_o = sqrt(g.sum(s));
+    *f_diff_o = fabs(newf - fval);
+    *newf_o = newf;
+    return flag;
+  }
+
   // ------------------------------------------------------------ the driver (optimize.jl:176-443)
   LFPSQP_DEV void run(const BatchedArgs &A, int64_t k) {
     fc.prm = A.fam_params ? A.fam_params + k * A.fam_stride : nullptr;
@@ -591,7 +667,9 @@ struct Solver {
       if (ME > 0) kind = (!prm.do_project_retract) ? 2 : 3;                // rank == m here (full rank or stopped)
       else kind = ineq ? 1 : 0;
       double newf;
-      int flag = armijo(kind, fval, &newf, &f_diff, &step_diff);
+      int flag;                                                            // :415-420
+      if (prm.linesearch == 0 || prm.disable_linesearch) flag = armijo(kind, fval, &newf, &f_diff, &step_diff);
+      else flag = exact_linesearch(kind, fval, &newf, &f_diff, &step_diff);
       st.flag_last = flag;
       copy(x, xnew, N);                                                    // :424-426
       fval = newf;
@@ -616,7 +694,7 @@ struct Solver {
 template <class Fam>
 __global__ void __launch_bounds__(256, 2) batched_warp_kernel(const BatchedArgs A, const int use_nr) {
   extern __shared__ double smem[];
-  const WarpLayout L(A.n, A.m, A.p, A.ineq, use_nr);
+  const WarpLayout L(A.n, A.m, A.p, A.ineq, use_nr, (A.prm.linesearch != 0 && !A.prm.disable_linesearch) ? 1 : 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   // CTA-shared copy of the bound data
   double *bnd = smem;

@@ -433,6 +433,95 @@ static int retract_nr(lfpsqp_ctx *c, LargeState &S, int *flag_out, int *it1) {
   return 0;
 }
 
+// ------------------------------------------------------------------ exact_linesearch! (linesearch.jl:107-339), host control flow
+static int exact_linesearch(lfpsqp_ctx *c, LargeState &S, int kind, double fval, double *newf_o, double *f_diff_o,
+                            double *step_diff_o, int *flag_o) {
+  const int64_t n = S.n_loc;
+  const lfpsqp_params &prm = S.prm;
+  const double phi1 = (3.0 - sqrt(5.0)) / 2.0, phi2 = (sqrt(5.0) - 1.0) / 2.0, phi3 = (sqrt(5.0) + 1.0) / 2.0;
+  double Delta = prm.alpha, f_a = 0, f_b = 0, f_c = 0, f_d = 0, a_a = 0, a_b = 0, a_c = 0, a_d = 0;
+  double *x_a = S.ex[0], *x_b = S.ex[1], *x_c = S.ex[2], *x_d = S.ex[3], *swp;
+  const double *x = S.x, *d = S.d; double *xtil = S.xtil, *xnew = S.xnew;
+  bool do_shrinking = true;
+  int flag = 0, rc = 0;
+  auto TRIAL = [&](double *pt, double al) {
+    vec(S, n, [=] __device__(int64_t i, double *) { xtil[i] = x[i] + al * d[i]; });
+    int i1 = 0, i2 = 0;
+    if (kind == 0) { cudaMemcpyAsync(xnew, xtil, n * 8, cudaMemcpyDeviceToDevice, S.stream); flag = 0; }
+    else if (kind == 2) rc |= retract_nr(c, S, &flag, &i1);
+    else rc |= retract_pp(c, S, &flag, &i1, &i2);
+    S.retract_outer += i1; S.retract_pcg += i2; S.armijo_trials++;
+    cudaMemcpyAsync(pt, xnew, n * 8, cudaMemcpyDeviceToDevice, S.stream);
+  };
+  auto FVAL = [&](const double *pt) -> double {
+    fam_f(S, pt); finalize(S, 1u, 0);
+    if (read_ctrl(c, S)) { rc = -1; return NAN; }
+    return S.hctrl->s[0];
+  };
+  cudaMemcpyAsync(x_d, x, n * 8, cudaMemcpyDeviceToDevice, S.stream); f_d = fval;
+  while (true) {
+    swp = x_b; x_b = x_c; x_c = x_d; x_d = swp;
+    f_b = f_c; f_c = f_d; a_b = a_c; a_c = a_d;
+    TRIAL(x_d, a_d + Delta);
+    a_d += Delta;
+    if (rc) return -1;
+    if (flag > 0 || a_d > 1.0) { f_d = INFINITY; break; }
+    f_d = FVAL(x_d);
+    if (f_d > f_c) break;
+    do_shrinking = false;
+    Delta *= phi3;
+  }
+  if (do_shrinking) {
+    f_b = fval; a_b = 0.0; cudaMemcpyAsync(x_b, x, n * 8, cudaMemcpyDeviceToDevice, S.stream);
+    f_c = INFINITY; a_c = Delta;
+    swp = x_d; x_d = x_c; x_c = swp;
+    while (true) {
+      swp = x_d; x_d = x_c; x_c = swp;
+      f_d = f_c; a_d = a_c;
+      TRIAL(x_c, phi1 * a_c);
+      a_c *= phi1;
+      if (rc) return -1;
+      if (flag > 0 || a_c > 1.0) f_c = INFINITY; else f_c = FVAL(x_c);
+      if (f_c <= fval || a_c < 1e-100) break;
+    }
+  }
+  f_a = f_b; f_b = f_c; a_a = a_b; a_b = a_c;
+  swp = x_a; x_a = x_b; x_b = x_c; x_c = swp;
+  a_c = a_a + phi2 * (a_d - a_a);
+  TRIAL(x_c, a_c);
+  if (rc) return -1;
+  if (flag > 0 || a_c > 1.0) f_c = INFINITY; else f_c = FVAL(x_c);
+  vec(S, n, [=] __device__(int64_t i, double *acc) { acc[0] += d[i] * d[i]; }, 0, 1);
+  finalize(S, 1u, 0);
+  if (read_ctrl(c, S)) return -1;
+  const double nd_ = sqrt(S.hctrl->s[0]);
+  while ((a_c - a_b) > 1e-6 * nd_) {
+    if (f_b < f_c || isinf(f_c)) {
+      swp = x_d; x_d = x_c; x_c = x_b; x_b = swp;
+      f_d = f_c; f_c = f_b; a_d = a_c; a_c = a_b;
+      a_b = a_a + phi1 * (a_d - a_a);
+      TRIAL(x_b, a_b);
+      f_b = FVAL(x_b);
+    } else {
+      swp = x_a; x_a = x_b; x_b = x_c; x_c = swp;
+      f_a = f_b; f_b = f_c; a_a = a_b; a_b = a_c;
+      a_c = a_a + phi2 * (a_d - a_a);
+      TRIAL(x_c, a_c);
+      if (flag > 0 || a_c > 1.0) f_c = INFINITY; else f_c = FVAL(x_c);
+    }
+    if (rc) return -1;
+  }
+  (void)f_a; (void)f_d;
+  double newf;
+  if (f_b < f_c) { cudaMemcpyAsync(xnew, x_b, n * 8, cudaMemcpyDeviceToDevice, S.stream); newf = f_b; }
+  else { cudaMemcpyAsync(xnew, x_c, n * 8, cudaMemcpyDeviceToDevice, S.stream); newf = f_c; }
+  vec(S, n, [=] __device__(int64_t i, double *acc) { double t = xnew[i] - x[i]; acc[0] += t * t; }, 0, 1);
+  finalize(S, 1u, 0);
+  if (read_ctrl(c, S)) return -1;
+  *step_diff_o = sqrt(S.hctrl->s[0]); *f_diff_o = fabs(newf - fval); *newf_o = newf; *flag_o = flag;
+  return 0;
+}
+
 // ------------------------------------------------------------------ the driver (optimize.jl:119-443, no bounds)
 static int solve(lfpsqp_ctx *c, LargeState &S, const double *x0_host, double *x_out, double *obj_hist, int64_t H,
                  int64_t *obj_len, double *lambda, lfpsqp_term *term, lfpsqp_stats *stats) {
@@ -492,7 +581,9 @@ static int solve(lfpsqp_ctx *c, LargeState &S, const double *x0_host, double *x_
     double alpha = prm.alpha, newf = 0.0;
     f_diff = INFINITY; step_diff = INFINITY;
     int flag = 0;
-    while (step_diff > prm.eps_x) {
+    const bool exact = (prm.linesearch != 0 && !prm.disable_linesearch);                // :415-420
+    if (exact) { if (exact_linesearch(c, S, kind, fval, &newf, &f_diff, &step_diff, &flag)) return LFPSQP_ERR_CUDA; }
+    while (!exact && step_diff > prm.eps_x) {
       double al = alpha;
       vec(S, n, [=] __device__(int64_t i, double *) { xtil[i] = x[i] + al * d[i]; });
       int i1 = 0, i2 = 0;
@@ -640,8 +731,10 @@ static int need_large(lfpsqp_ctx *c) {
 static int prep_params(lfpsqp_ctx *c, LargeState &S, const lfpsqp_params *prm) {
   if (!prm) return c->fail(LFPSQP_ERR_ARG, "params is NULL");
   if (prm->beta > 0) return c->fail(LFPSQP_ERR_UNSUPPORTED, "beta>0 is not supported on the device path");
-  if (prm->linesearch != 0 && !prm->disable_linesearch) return c->fail(LFPSQP_ERR_UNSUPPORTED, "linesearch=exact is not on the device path yet");
   S.prm = *prm;
+  if (prm->linesearch != 0 && !prm->disable_linesearch && !S.ex[0]) {
+    for (int i = 0; i < 4; i++) if (!dalloc(S, &S.ex[i], (size_t)S.n_loc + 2)) return c->fail(LFPSQP_ERR_NOMEM, "exact line search workspace allocation failed");
+  }
   if (!prm->do_project_retract && S.m > 0 && !S.Dnr) {
     if (!dalloc(S, &S.Dnr, (size_t)S.m * S.ldm)) return c->fail(LFPSQP_ERR_NOMEM, "NR workspace allocation failed");
   }

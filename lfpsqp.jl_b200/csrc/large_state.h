@@ -22,7 +22,7 @@ struct LargeState {
   size_t gemm_ws_bytes = 0;
   // n_loc vectors
   double *x = nullptr, *xnew = nullptr, *xtil = nullptr, *g = nullptr, *d = nullptr, *nd = nullptr, *w0 = nullptr,
-         *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr, *hdiag = nullptr;
+         *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr, *hdiag = nullptr, *ex[4] = {nullptr, nullptr, nullptr, nullptr};
   // m vectors (replicated on every rank)
   double *cval = nullptr, *lam = nullptr, *tm = nullptr, *ty = nullptr, *tu = nullptr, *nr_t1 = nullptr, *nr_t2 = nullptr,
          *nr_dc = nullptr;

@@ -175,3 +175,36 @@ def test_register_and_shared_memory_kernels_agree(L, monkeypatch):
         x = L.optimize_batched(fam.f, None, fam.d, np.zeros((64, n2)), -inf2, inf2, 0, 1)[0]
         nc = np.linalg.norm(co, axis=1)
         assert np.max(np.linalg.norm(x + co / nc[:, None], axis=1)) < 1e-4
+
+
+def test_exact_linesearch_vs_oracle(L, oracle):
+    # exact_linesearch! (src/linesearch.jl:107-339), selected by param.linesearch == exact (optimize.jl:415-420)
+    prm = L.LFPSQPParams(linesearch=L.exact)
+    oprm = oracle.default_params(linesearch=1)
+    rng = np.random.default_rng(21)
+    # unconstrained (Euclidean retraction)
+    B = 256
+    x0 = rng.uniform(-2, 2, (B, 2)); x0[0] = 0.0
+    fam = L.families.rosenbrock()
+    gpu = L.optimize_batched(fam.f, x0, prm, history=256)
+    # golden-section decisions (f_b < f_c) amplify rounding: calibrate against oracle-vs-oracle(+fma)
+    orc, base = _sens(oracle, lambda: oracle.optimize_batched("rosenbrock", 2, 0, 0, x0, params=oprm, H=256, nthreads=8), 2, "rosenbrock exact")
+    _require(compare_batch(gpu, orc, 2, "rosenbrock exact"), 0.97, base)
+    # slack + bounds + ProjPenalty retraction
+    B, n = 128, 50
+    co = rng.standard_normal((B, n)); inf = np.inf * np.ones(n)
+    fam = L.families.readme_inequality(co)
+    gpu = L.optimize_batched(fam.f, None, fam.d, np.zeros((B, n)), -inf, inf, 0, 1, prm)
+    orc, base = _sens(oracle, lambda: oracle.optimize_batched("readme_ineq", n, 0, 1, np.zeros((B, n)), xl=-inf, xu=inf, fam_params=co,
+                                                             fam_stride=n, params=oprm, nthreads=8), n, "readme_ineq exact")
+    _require(compare_batch(gpu, orc, n, "readme_ineq exact"), 0.97, base)
+    # equality constraints with NR and PP
+    B, n, m = 64, 24, 6
+    t = rng.standard_normal((B, n))
+    fam = L.families.sin_system(n, m, t)
+    for nr in (False, True):
+        gpu = L.optimize_batched(fam.f, fam.c, np.zeros((B, n)), m, L.LFPSQPParams(linesearch=L.exact, do_project_retract=not nr))
+        orc, base = _sens(oracle, lambda: oracle.optimize_batched("sin", n, m, 0, np.zeros((B, n)), fam_params=t, fam_stride=n,
+                                                                 params=oracle.default_params(linesearch=1, do_project_retract=0 if nr else 1),
+                                                                 nthreads=8), n, "sin exact")
+        _require(compare_batch(gpu, orc, n, "sin exact nr=%s" % nr), 0.95, base)

@@ -155,3 +155,17 @@ def test_full_size_properties_c5(L):
     assert rel(pv2, pv) < 1e-12
     r = P.projcg(x0h, lam=np.zeros(m), tol=0.0, maxit=8, want_solution=False)
     assert r["iters"] == 8 and r["status"] == 4
+
+
+def test_exact_linesearch_large_vs_oracle(L, oracle):
+    # exact_linesearch! (src/linesearch.jl:107-339) in large-n mode
+    n, m = 1000, 60
+    Q, A, b, xt, w, x0 = L.make_diagquad(n, m, seed=9, cond=100.0)
+    fam = L.families.diagquad(Q, A, b, xt, w)
+    x, obj, lam, info, st, status = L.LargeProblem(fam).solve(x0, L.LFPSQPParams(linesearch=L.exact), return_stats=True)
+    ox, oobj, olam, ot, ost = oracle.optimize("diagquad", n, m, 0, x0, fam_params=fam.params, params=oracle.default_params(linesearch=1))
+    with oracle.variant("fma"):   # rounding sensitivity of the golden-section decisions: oracle vs oracle(+fma)
+        fx, fobj, _, ft, _ = oracle.optimize("diagquad", n, m, 0, x0, fam_params=fam.params, params=oracle.default_params(linesearch=1))
+    assert status == 0 and int(info.condition) == ot["condition"] and abs(info.iter - ot["iter"]) <= 1
+    assert rel(x, ox) <= max(1e-8, 10 * rel(fx, ox))
+    assert abs(obj[-1] - oobj[-1]) <= max(1e-10, 10 * abs(fobj[-1] - oobj[-1]) / abs(oobj[-1])) * abs(oobj[-1])
