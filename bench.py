@@ -208,6 +208,72 @@ def large_n_section(L, ctx, torch, dev, with_cpu, dist=None, rank=0, world=1):
     return out
 
 
+def extras_section(L, ctx, torch, dev, with_cpu):
+    """Parity-test configurations of BASELINE.json reported as extra lines (not the headline): C3 Rosenbrock batched
+    (1,048,576 instances, thread-per-instance kernel) and C4 Thomson N=4096 (n=12288, m=4096, J treated dense as the
+    reference does) -- first 10 outer iterations of the real solve, split by phase."""
+    import ctypes as C
+    from lfpsqp.jl_b200 import _lib
+    out = {}
+    # ---- C3
+    B = 1 << 20
+    rng = np.random.Generator(np.random.Philox(key=SEED + 3))
+    x0 = rng.uniform(-2.0, 2.0, (B, 2)); x0[0] = 0.0            # instance 0 = the README start (golden vector)
+    H = 64
+    d_x0 = torch.from_numpy(x0).to(dev); d_x = torch.empty((B, 2), dtype=torch.float64, device=dev)
+    d_obj = torch.empty((B, H), dtype=torch.float64, device=dev); d_len = torch.empty(B, dtype=torch.int64, device=dev)
+    d_lam = torch.empty((B, 1), dtype=torch.float64, device=dev); d_term = torch.empty(B * 40, dtype=torch.uint8, device=dev)
+    prm = L.LFPSQPParams(disp=L.off).to_c(); pprm = C.cast(C.pointer(prm), C.c_void_p)
+    ms = []
+    for k in range(6):
+        ctx.check(ctx.lib.lfpsqp_solve_batched_dev(ctx.h, L.families.ROSENBROCK, 2, 0, 0, B, None, 0, d_x0.data_ptr(), None, None, pprm,
+                                                   d_x.data_ptr(), d_obj.data_ptr(), H, d_len.data_ptr(), d_lam.data_ptr(), d_term.data_ptr(), None))
+        if k >= 2:
+            ms.append(ctx.last_kernel_ms)
+    lens = d_len.cpu().numpy()
+    term0 = np.frombuffer(d_term[:40].cpu().numpy().tobytes(), dtype=_lib.TERM_DTYPE)[0]
+    kms = float(np.median(ms))
+    io = float(B * (16 + 16 + 8 + 40) + 8 * np.minimum(lens, H).sum())
+    out["c3_rosenbrock_batched"] = {"metric": "SQP instances solved/sec", "value": B / (kms * 1e-3), "unit": UNIT, "instances": B,
+                                    "kernel": "batched_tiny_kernel<FamRosenbrock,2> (one thread per instance)", "kernel_ms": kms,
+                                    "mean_outer_iterations": float(lens.mean() - 1),
+                                    "golden_instance0": {"iter": int(term0["iter"]), "condition": int(term0["condition"]), "f_diff": float(term0["f_diff"])},
+                                    "hbm_io_gbs": io / (kms * 1e-3) / 1e9}
+    if with_cpu:
+        from oracle import oracle as O
+        S = 1 << 17
+        t0 = time.perf_counter()
+        O.optimize_batched("rosenbrock", 2, 0, 0, x0[:S], H=H, nthreads=host_cores())
+        dt = time.perf_counter() - t0
+        out["c3_rosenbrock_batched"]["cpu_baseline"] = {"value": S / dt, "unit": UNIT, "cores": host_cores(), "kind": "port",
+                                                        "sample": "%d of the %d instances" % (S, B)}
+    del d_x0, d_x, d_obj, d_len, d_lam, d_term
+    # ---- C4
+    npts = 4096
+    rng = np.random.Generator(np.random.Philox(key=SEED + 4))
+    p0 = rng.standard_normal((npts, 3)); p0 /= np.linalg.norm(p0, axis=1, keepdims=True)
+    P = L.LargeProblem(L.families.thomson(npts), ctx)
+    gram_ms = min(P.factor(p0.ravel(), want=())["gram_ms"] for _ in range(2))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        t0 = time.perf_counter()
+        x, obj, lam, info, st, status = P.solve(p0.ravel(), L.LFPSQPParams(maxiter=10, disp=L.off), return_stats=True)
+        wall = time.perf_counter() - t0
+    ph = P.phase_ms()
+    n, m = 3 * npts, npts
+    bytes_it = 16.0 * m * n + 8.0 * m * m + 104.0 * n
+    it_s = st["projcg_iters"] / (ph["projcg"] * 1e-3) if ph["projcg"] > 0 else None
+    out["c4_thomson_4096"] = {"workload": "Thomson N=4096: n=12288, m=4096, dense J (402 MB), first 10 outer iterations, default params",
+                              "outer_iterations": info.iter, "wall_s": wall, "phase_ms": ph, "stats": st, "status": status,
+                              "f_first_last": [float(obj[0]), float(obj[-1])],
+                              "gram": {"ms": gram_ms, "tflops": m * (m + 1.0) * n / (gram_ms * 1e-3) / 1e12},
+                              "projcg_iterations_per_s_in_solve": it_s,
+                              "projcg_roofline_frac_in_solve": (bytes_it * it_s / 1e9 / 6543.4) if it_s else None,
+                              "note": "in-solve projcg rate includes the start-up projection, Thomson's O(N^2) pairwise Hessian kernel and one host sync per chunk"}
+    return out
+
+
 def run_reference(args):
     """Reference arm: the reference's CPU implementation of the path = the oracle port (kind "port"), all host threads,
     same config/metric; each step is a bounded sample of the workload."""
@@ -412,6 +478,11 @@ def main():
                                               dist, rank, world)
         except Exception as e:  # noqa
             line["large_n"] = {"error": repr(e)}
+    if world == 1 and not args.skip_large:
+        try:
+            line["extras"] = extras_section(L, ctx, torch, dev, not args.no_cpu_baseline)
+        except Exception as e:  # noqa
+            line["extras"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -155,6 +155,10 @@ int lfpsqp_large_retract(lfpsqp_ctx *ctx, int method, const double *x_base_loc, 
 int lfpsqp_large_pcg(lfpsqp_ctx *ctx, const double *x_point_loc, double mu, const double *b_loc, double tol, int64_t maxiter,
                      double *x_out_loc, double *r_out_loc, int *flag, int64_t *iters);
 
+/* host wall-clock split (ms) of the last lfpsqp_large_solve: [factorisation (jac!, Gram, Cholesky, first projection),
+ * projcg!, line search incl. retractions, total] */
+int lfpsqp_large_phase_ms(lfpsqp_ctx *ctx, double *out4);
+
 /* Unit-level bound embedding (src/inequality_helper.jl; y_retract! src/retractions.jl:451-500) on one instance; runs the
  * device code of the batched solver.  J: m x n row-major (== Jct column-major), may be NULL when m = 0.
  *  op 0 generate_initial_y! (:92-109)   in x (n)                          out xaug (2n)

@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "ctx.h"
@@ -27,6 +28,9 @@ using namespace lfpsqp;
   } while (0)
 
 static inline int64_t up2(int64_t v) { return (v + 1) & ~(int64_t)1; }
+static inline double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 // ------------------------------------------------------------------ small launch helpers
 template <class F>
@@ -108,16 +112,21 @@ static void gram_solve(LargeState &S, const double *t, double *u, double *u_copy
 }
 
 // ------------------------------------------------------------------ family dispatch (device callbacks, whole-GPU kernels)
+static void thomson_grid(LargeState &S, int np, dim3 &grid) {
+  int ib = (np + 255) / 256;
+  int js = std::max(1, std::min(16, (2 * S.sm_count) / ib));
+  grid = dim3(ib, js);
+}
 static void fam_f(LargeState &S, const double *x) {  // -> gpart slot 0 (sum); caller finalizes s[0]
   if (S.family == LFPSQP_FAM_DIAGQUAD) {
     const double *xt = S.p_xt, *w = S.p_w;
     vec(S, S.n_loc, [=] __device__(int64_t j, double *acc) { double t = x[j] - xt[j]; acc[0] += 0.5 * w[j] * t * t; }, 0, 1);
   } else {
     int np = (int)(S.n / 3);
-    thomson_pair_kernel<0><<<(np + 255) / 256, 256, 0, S.stream>>>(np, x, nullptr, nullptr, nullptr, S.gpart, 0, S.ctrl, 0);
-    // the pair kernel wrote (np+255)/256 partials; zero the rest of the slot so that finalize's fixed np is right
-    int used = (np + 255) / 256; double *gp = S.gpart; int vg = S.vgrid;
-    if (used < vg) vec(S, vg - used, [=] __device__(int64_t e, double *) { gp[used + e] = 0.0; });
+    dim3 grid; thomson_grid(S, np, grid);
+    thomson_pair_kernel<0><<<grid, 256, 0, S.stream>>>(np, x, nullptr, nullptr, S.gpart, 0, S.ctrl, 0);
+    // the pair kernel wrote grid.x*grid.y partials: fold them into the vgrid partials finalize() expects
+    collapse_partials_kernel<<<1, 256, 0, S.stream>>>(S.gpart, grid.x * grid.y, S.vgrid);
   }
   S.launches++; S.f_evals++;
 }
@@ -127,7 +136,10 @@ static void fam_grad(LargeState &S, double *g, const double *x) {
     vec(S, S.n_loc, [=] __device__(int64_t j, double *) { g[j] = w[j] * (x[j] - xt[j]); });
   } else {
     int np = (int)(S.n / 3);
-    thomson_pair_kernel<1><<<(np + 255) / 256, 256, 0, S.stream>>>(np, x, nullptr, nullptr, g, nullptr, 0, S.ctrl, 0);
+    dim3 grid; thomson_grid(S, np, grid);
+    thomson_pair_kernel<1><<<grid, 256, 0, S.stream>>>(np, x, nullptr, S.pairws, nullptr, 0, S.ctrl, 0);
+    thomson_reduce_kernel<1><<<(3 * np + 255) / 256, 256, 0, S.stream>>>(np, grid.y, S.pairws, nullptr, nullptr, g, nullptr, 0, S.ctrl, 0);
+    S.launches++;
   }
   S.launches++;
 }
@@ -171,9 +183,11 @@ static int fam_hess(LargeState &S, double *dest, const double *src, const double
     return S.vgrid;
   } else {
     int np = (int)(S.n / 3);
-    thomson_pair_kernel<2><<<(np + 255) / 256, 256, 0, S.stream>>>(np, x, src, lam, dest, S.lp, 0, S.ctrl, pred);
-    S.launches++;
-    return (np + 255) / 256;
+    dim3 grid; thomson_grid(S, np, grid);
+    thomson_pair_kernel<2><<<grid, 256, 0, S.stream>>>(np, x, src, S.pairws, nullptr, 0, S.ctrl, pred);
+    thomson_reduce_kernel<2><<<(3 * np + 255) / 256, 256, 0, S.stream>>>(np, grid.y, S.pairws, src, lam, dest, S.lp, 0, S.ctrl, pred);
+    S.launches += 2;
+    return (3 * np + 255) / 256;
   }
 }
 
@@ -546,14 +560,17 @@ static int solve(lfpsqp_ctx *c, LargeState &S, const double *x0_host, double *x_
     vec(S, n, [=] __device__(int64_t i, double *) { d[i] = -1.0 * g[i]; });              // :262
     S.launches++;
     if (m > 0) {
+      const double tf0 = now_ms();
       fam_c_jac(S, S.J, S.cval, x);                                                     // :283
       if (factorize(c, S)) return LFPSQP_ERR_CUDA;
       project(S, d, S.lam, 0, 1);                                                       // :306-307, :333-343
+      S.t_factor_pending = tf0;
     } else {
       vec(S, n, [=] __device__(int64_t i, double *acc) { double r = d[i]; acc[0] += r * r; acc[3] = nanmax(acc[3], fabs(r)); }, 0, 1, 1);
     }
     finalize(S, 1u, 8u);
     if (read_ctrl(c, S)) return LFPSQP_ERR_CUDA;
+    if (S.t_factor_pending > 0) { S.ms_factor += now_ms() - S.t_factor_pending; S.t_factor_pending = 0; }
     if (S.hctrl->rankflag) { status |= LFPSQP_ST_RANK_DEFICIENT; cond = LFPSQP_MAX_ITER; break; }
     kkt_diff = S.hctrl->s[3];                                                           // :320
     double gn = sqrt(S.hctrl->s[0]);
@@ -565,8 +582,10 @@ static int solve(lfpsqp_ctx *c, LargeState &S, const double *x0_host, double *x_
     if (prm.do_newton) {                                                                // :364-390
       double tol = prm.tn_kappa * fmin(1.0, gn / prev_grad_norm) * gn;
       prev_grad_norm = gn;
+      const double tp0 = now_ms();
       fam_hess_prepare(S, x, S.lam);
       if (projcg(c, S, tol, prm.tn_maxiter, S.cg_chunk)) return LFPSQP_ERR_CUDA;
+      S.ms_projcg += now_ms() - tp0;
       vec(S, n, [=] __device__(int64_t i, double *acc) { acc[0] += nd[i] * d[i]; }, 0, 1);
       finalize(S, 1u, 0);
       if (read_ctrl(c, S)) return LFPSQP_ERR_CUDA;
@@ -581,6 +600,7 @@ static int solve(lfpsqp_ctx *c, LargeState &S, const double *x0_host, double *x_
     double alpha = prm.alpha, newf = 0.0;
     f_diff = INFINITY; step_diff = INFINITY;
     int flag = 0;
+    const double tl0 = now_ms();
     const bool exact = (prm.linesearch != 0 && !prm.disable_linesearch);                // :415-420
     if (exact) { if (exact_linesearch(c, S, kind, fval, &newf, &f_diff, &step_diff, &flag)) return LFPSQP_ERR_CUDA; }
     while (!exact && step_diff > prm.eps_x) {
@@ -605,6 +625,7 @@ static int solve(lfpsqp_ctx *c, LargeState &S, const double *x0_host, double *x_
       if (alpha < 1e-100) { flag = 99; break; }
     }
     last_flag = flag;
+    S.ms_linesearch += now_ms() - tl0;
     cudaMemcpyAsync(x, xnew, n * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);    // :424
     fval = newf;
     if (nobj < H) obj_hist[nobj] = fval;
@@ -693,6 +714,7 @@ extern "C" int lfpsqp_large_setup(lfpsqp_ctx *c, int family, int64_t n_global, i
   ok &= dalloc(S, &S.cpart, (size_t)S.nsplit * std::max(nl, mm) + 2);
   ok &= dalloc(S, &S.lp, (size_t)NSLOT * MAXP); ok &= dalloc(S, &S.gpart, (size_t)NSLOT * MAXP);
   ok &= dalloc(S, &S.ctrl, 1); ok &= dalloc(S, &S.commbuf, 64);
+  if (family == LFPSQP_FAM_THOMSON) ok &= dalloc(S, &S.pairws, (size_t)16 * nl + 2);
   S.Dnr = nullptr;
   if (!ok) { lfpsqp_large_release(c); return c->fail(LFPSQP_ERR_NOMEM, "large-n setup: device allocation failed"); }
   if (cudaMallocHost((void **)&S.hctrl, sizeof(LargeCtrl)) != cudaSuccess) { lfpsqp_large_release(c); return c->fail(LFPSQP_ERR_NOMEM, "pinned allocation failed"); }
@@ -895,5 +917,13 @@ extern "C" int lfpsqp_large_pcg(lfpsqp_ctx *c, const double *x_point_loc, double
   if (iters) *iters = S.hctrl->pcg_iter;
   if (flag) *flag = (S.hctrl->pcg_iter == maxiter) ? 1 : 0;
   c->last_launches = S.launches;
+  return LFPSQP_OK;
+}
+
+// host wall-clock split of the last lfpsqp_large_solve (every phase starts and ends at a host<->device sync):
+// out = [factorisation incl. jac!/Gram/Cholesky/first projection, projcg!, line search incl. retractions, total device ms]
+extern "C" int lfpsqp_large_phase_ms(lfpsqp_ctx *c, double *out4) {
+  if (!c || !c->large || !out4) return LFPSQP_ERR_ARG;
+  out4[0] = c->large->ms_factor; out4[1] = c->large->ms_projcg; out4[2] = c->large->ms_linesearch; out4[3] = c->last_ms;
   return LFPSQP_OK;
 }

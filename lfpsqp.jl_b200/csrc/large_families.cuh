@@ -65,26 +65,28 @@ __global__ void __launch_bounds__(256) dq_rows_kernel(const double *__restrict__
 }
 
 // ================================================================== THOMSON (BASELINE config C4), single-GPU shard
-// One thread per point i, all points j streamed through shared memory in tiles of 256.
-// mode 0: f partials (sum_{j!=i} 1/r_ij, halved)      -> part slot s0
-// mode 1: gradient g_i = -sum_j (x_i-x_j)/r^3
-// mode 2: Hessian action dest_i = sum_j [3 r (r.w)/r^5 - w/r^3] + 2 lam_i v_i  (w = v_i - v_j) and partial v.dest -> slot s0
+// Pairwise O(N^2) kernels on a 2-D grid: blockIdx.x = block of 256 points i, blockIdx.y = chunk of the j range (so
+// that N = 4096 fills the GPU: 16 x 16 CTAs instead of 16).  Points j are staged through shared memory.
+// mode 0: f partials (sum_{j!=i} 1/r_ij, halved)                       -> part slot s0 [blockIdx.y * gridDim.x + blockIdx.x]
+// mode 1: partial gradient   -sum_j (x_i-x_j)/r^3                      -> ws[blockIdx.y][3 i ..]
+// mode 2: partial Hessian action sum_j [3 r (r.w)/r^5 - w/r^3], w = v_i - v_j  -> ws[blockIdx.y][3 i ..]
 template <int MODE>
 __global__ void __launch_bounds__(256) thomson_pair_kernel(int np_, const double *__restrict__ x, const double *__restrict__ v,
-                                                           const double *__restrict__ lam, double *__restrict__ out,
-                                                           double *part, int s0, const LargeCtrl *ctrl, int pred) {
+                                                           double *__restrict__ ws, double *part, int s0,
+                                                           const LargeCtrl *ctrl, int pred) {
   if (pred == 1 && ctrl->status != 0) return;
   __shared__ double xs[256 * 3];
   __shared__ double vs[MODE == 2 ? 256 * 3 : 3];
   __shared__ double sh[33];
   const int i = blockIdx.x * 256 + threadIdx.x;
   const bool act = i < np_;
+  const int jlen = (np_ + gridDim.y - 1) / gridDim.y, jbeg = blockIdx.y * jlen, jend = min(np_, jbeg + jlen);
   double xi = 0, yi = 0, zi = 0, vx = 0, vy = 0, vz = 0;
   if (act) { xi = x[3 * i]; yi = x[3 * i + 1]; zi = x[3 * i + 2]; if (MODE == 2) { vx = v[3 * i]; vy = v[3 * i + 1]; vz = v[3 * i + 2]; } }
   double a0 = 0, a1 = 0, a2 = 0;
-  for (int j0 = 0; j0 < np_; j0 += 256) {
+  for (int j0 = jbeg; j0 < jend; j0 += 256) {
     __syncthreads();
-    int jn = min(256, np_ - j0);
+    int jn = min(256, jend - j0);
     for (int e = threadIdx.x; e < jn * 3; e += 256) { xs[e] = x[3 * j0 + e]; if (MODE == 2) vs[e] = v[3 * j0 + e]; }
     __syncthreads();
     if (act) {
@@ -102,16 +104,31 @@ __global__ void __launch_bounds__(256) thomson_pair_kernel(int np_, const double
       }
     }
   }
-  double pr = 0.0;
-  if (MODE == 0) pr = act ? 0.5 * a0 : 0.0;
-  else if (MODE == 1) { if (act) { out[3 * i] = a0; out[3 * i + 1] = a1; out[3 * i + 2] = a2; } }
-  else if (act) {
-    double l2 = 2.0 * lam[i];
-    a0 += l2 * vx; a1 += l2 * vy; a2 += l2 * vz;
-    out[3 * i] = a0; out[3 * i + 1] = a1; out[3 * i + 2] = a2;
-    pr = vx * a0 + vy * a1 + vz * a2;
+  if (MODE == 0) {
+    double pr = block_sum(act ? 0.5 * a0 : 0.0, sh);
+    if (threadIdx.x == 0) part[(size_t)s0 * MAXP + blockIdx.y * gridDim.x + blockIdx.x] = pr;
+  } else if (act) {
+    double *o = ws + (size_t)blockIdx.y * 3 * np_ + 3 * i;
+    o[0] = a0; o[1] = a1; o[2] = a2;
   }
-  if (MODE != 1) {
+}
+// sums the j-chunk partials; mode 2 adds the constraint part 2 lam_i v_i and writes the v.dest partial (loop slot 0)
+template <int MODE>
+__global__ void __launch_bounds__(256) thomson_reduce_kernel(int np_, int chunks, const double *__restrict__ ws,
+                                                             const double *__restrict__ v, const double *__restrict__ lam,
+                                                             double *__restrict__ out, double *part, int s0,
+                                                             const LargeCtrl *ctrl, int pred) {
+  if (pred == 1 && ctrl->status != 0) return;
+  __shared__ double sh[33];
+  const int e = blockIdx.x * 256 + threadIdx.x, n3 = 3 * np_;
+  double pr = 0.0;
+  if (e < n3) {
+    double s = 0.0;
+    for (int k = 0; k < chunks; k++) s += ws[(size_t)k * n3 + e];
+    if (MODE == 2) { double ve = v[e]; s += 2.0 * lam[e / 3] * ve; pr = ve * s; }
+    out[e] = s;
+  }
+  if (MODE == 2) {
     pr = block_sum(pr, sh);
     if (threadIdx.x == 0) part[(size_t)s0 * MAXP + blockIdx.x] = pr;
   }

@@ -140,51 +140,100 @@ __global__ void __launch_bounds__(256) dgemm_nt_kernel(int M, int N, int K, cons
 template <int BN> constexpr size_t dgemm_smem_bytes() { return (size_t)GM_STAGES * (GM_BM + BN) * GM_LD * sizeof(double); }
 
 // ------------------------------------------------------------------ diagonal block: in-shared-memory Cholesky + inverse
-// One CTA factors the NB x NB diagonal block of A (row-major, lda) in shared memory, writes L_jj back (zeros above
-// the diagonal) and D = L_jj^-1 (row-major NB x NB, zeros above the diagonal) to Dout.  nb_act <= NB rows are active.
+// One CTA (256 threads as a 16 x 16 grid, each owning a 4 x 4 register tile) factors the 64 x 64 diagonal block of A
+// (row-major, lda): right-looking Cholesky with the current column broadcast through shared memory (2 barriers per
+// column), then D = L_jj^-1 by a blocked triangular inversion (16 x 16 diagonal blocks by forward substitution,
+// off-diagonal blocks by two small products per block).  Writes L_jj back (zeros above the diagonal) and D
+// (row-major NB x NB, zeros above the diagonal and outside nb_act) to Dout.
 // flag[0] is set to 1 when a pivot is not > thresh (rank deficiency, cf. optimize.jl:297-302).
 template <int NB>
 __global__ void __launch_bounds__(256) potf2_inv_kernel(double *A, int64_t lda, int nb_act, double *Dout,
                                                         const double *thresh_p, int *flag) {
+  static_assert(NB == 64, "register tiling assumes a 64 x 64 block");
   extern __shared__ double psm[];
   double (*Ls)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(psm);
   double (*Ds)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(psm + NB * (NB + 1));
-  const int tid = threadIdx.x;
+  __shared__ double colbuf[NB];
+  __shared__ double Ts[16][17];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const double thresh = thresh_p[0];
-  for (int e = tid; e < NB * NB; e += 256) {
-    int r = e / NB, c = e % NB;
-    Ls[r][c] = (r < nb_act && c < nb_act) ? A[(int64_t)r * lda + c] : (r == c ? 1.0 : 0.0);
-  }
-  __syncthreads();
-  for (int k = 0; k < nb_act; k++) {
-    double piv = Ls[k][k];
+  double a[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      int gr = 4 * ty + r, gc = 4 * tx + c;
+      a[r][c] = (gr < nb_act && gc < nb_act) ? A[(int64_t)gr * lda + gc] : (gr == gc ? 1.0 : 0.0);
+    }
+  for (int k = 0; k < NB; k++) {
+    const int kb = k >> 2, kk = k & 3;
+    if (tx == kb) {   // owners of column k publish it (unscaled)
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) if (c == kk) colbuf[4 * ty + r] = a[r][c];
+    }
     __syncthreads();
-    if (!(piv > thresh)) { if (tid == 0) flag[0] = 1; piv = (piv > 0.0) ? piv : 1.0; }
-    double d = sqrt(piv);
-    if (tid == 0) Ls[k][k] = d;
-    for (int i = k + 1 + tid; i < nb_act; i += 256) Ls[i][k] = Ls[i][k] / d;
-    __syncthreads();
-    // trailing update of the lower triangle: A[i][j] -= L[i][k] L[j][k], k < j <= i
-    int rem = nb_act - k - 1;
-    for (int e = tid; e < rem * rem; e += 256) {
-      int i = k + 1 + e / rem, j = k + 1 + e % rem;
-      if (j <= i) Ls[i][j] -= Ls[i][k] * Ls[j][k];
+    double piv = colbuf[k];
+    if (!(piv > thresh)) { if (tid == 0 && k < nb_act) flag[0] = 1; piv = (piv > 0.0) ? piv : 1.0; }
+    const double d = sqrt(piv), dinv = 1.0 / d;
+    double lr[4], lc[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) { int gr = 4 * ty + r; lr[r] = (gr > k) ? colbuf[gr] * dinv : 0.0; }
+#pragma unroll
+    for (int c = 0; c < 4; c++) { int gc = 4 * tx + c; lc[c] = (gc > k) ? colbuf[gc] * dinv : 0.0; }
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) a[r][c] -= lr[r] * lc[c];
+    if (tx == kb) {   // store the scaled column into the owners' registers
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) if (c == kk) { int gr = 4 * ty + r; a[r][c] = (gr > k) ? lr[r] : (gr == k ? d : a[r][c]); }
     }
     __syncthreads();
   }
-  // D = L^-1 : column c by forward substitution, one column per thread
-  for (int c = tid; c < NB; c += 256) {
-    for (int i = 0; i < NB; i++) {
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      int gr = 4 * ty + r, gc = 4 * tx + c;
+      Ls[gr][gc] = (gc <= gr) ? a[r][c] : 0.0;
+      Ds[gr][gc] = 0.0;
+    }
+  __syncthreads();
+  // phase 1: the four 16 x 16 diagonal blocks, one column per thread (64 threads)
+  if (tid < 64) {
+    const int b = tid >> 4, c = tid & 15, o = 16 * b;
+    for (int i = c; i < 16; i++) {
       double s = (i == c) ? 1.0 : 0.0;
-      if (i < c) { Ds[i][c] = 0.0; continue; }
-      for (int t = c; t < i; t++) s -= Ls[i][t] * Ds[t][c];
-      Ds[i][c] = s / Ls[i][i];
+      for (int t = c; t < i; t++) s -= Ls[o + i][o + t] * Ds[o + t][o + c];
+      Ds[o + i][o + c] = s / Ls[o + i][o + i];
     }
   }
   __syncthreads();
+  // phase 2: off-diagonal blocks by increasing block distance: D_ij = -D_ii * (sum_{k=j}^{i-1} L_ik D_kj)
+  for (int dist = 1; dist < 4; dist++) {
+    for (int j = 0; j + dist < 4; j++) {
+      const int i = j + dist;
+      double t = 0.0;
+      for (int kb2 = j; kb2 < i; kb2++)
+#pragma unroll
+        for (int q = 0; q < 16; q++) t += Ls[16 * i + ty][16 * kb2 + q] * Ds[16 * kb2 + q][16 * j + tx];
+      Ts[ty][tx] = t;
+      __syncthreads();
+      double u = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; q++) u += Ds[16 * i + ty][16 * i + q] * Ts[q][tx];
+      __syncthreads();
+      Ds[16 * i + ty][16 * j + tx] = -u;
+    }
+    __syncthreads();
+  }
   for (int e = tid; e < NB * NB; e += 256) {
     int r = e / NB, c = e % NB;
-    if (r < nb_act && c < nb_act) A[(int64_t)r * lda + c] = (c <= r) ? Ls[r][c] : 0.0;
+    if (r < nb_act && c < nb_act) A[(int64_t)r * lda + c] = Ls[r][c];
     Dout[e] = (r < nb_act && c < nb_act) ? Ds[r][c] : 0.0;
   }
 }

@@ -187,6 +187,14 @@ __global__ void __launch_bounds__(256) finalize_kernel(const double *part, int n
   }
 }
 
+// part[0] = sum of the first `used` partials of slot 0, part[1..np) = 0  (single CTA, fixed order)
+__global__ void __launch_bounds__(256) collapse_partials_kernel(double *part, int used, int np) {
+  __shared__ double sh[33];
+  double r = reduce_partials(part, used, sh);
+  __syncthreads();
+  for (int i = threadIdx.x; i < max(np, used); i += 256) part[i] = (i == 0) ? r : 0.0;
+}
+
 // ------------------------------------------------------------------ generic fused elementwise kernel with up to 3 sum partials + 1 max
 // f(i, acc): elementwise body for index i; acc[0..2] are sum-reduced into slots s0..s0+2, acc[3] max-reduced into slot s0+3
 template <class F>

@@ -18,7 +18,7 @@ struct LargeState {
   const double *p_Q = nullptr, *p_A = nullptr, *p_b = nullptr, *p_xt = nullptr, *p_w = nullptr;
   // matrices
   double *J = nullptr, *G = nullptr, *XT = nullptr, *Linv = nullptr, *Dblk = nullptr, *tmp64 = nullptr, *thresh = nullptr,
-         *gemm_ws = nullptr, *Dnr = nullptr;
+         *gemm_ws = nullptr, *Dnr = nullptr, *pairws = nullptr;
   size_t gemm_ws_bytes = 0;
   // n_loc vectors
   double *x = nullptr, *xnew = nullptr, *xtil = nullptr, *g = nullptr, *d = nullptr, *nd = nullptr, *w0 = nullptr,
@@ -36,7 +36,9 @@ struct LargeState {
   // counters
   int64_t collectives = 0, launches = 0, projcg_iters = 0, projcg_negcurv = 0, armijo_trials = 0, retract_outer = 0, retract_pcg = 0,
           pp_backtracks = 0, newton_accepted = 0, factorizations = 0, f_evals = 0;
+  double ms_factor = 0, ms_projcg = 0, ms_linesearch = 0, t_factor_pending = 0;
   void reset_counters() {
+    ms_factor = ms_projcg = ms_linesearch = t_factor_pending = 0;
     launches = projcg_iters = projcg_negcurv = armijo_trials = retract_outer = retract_pcg = pp_backtracks = 0;
     newton_accepted = factorizations = f_evals = 0;
   }

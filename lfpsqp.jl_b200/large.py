@@ -40,6 +40,12 @@ class LargeProblem:
             return res + ({k: int(stats[0][k]) for k in _lib.STATS_FIELDS}, int(t["status"]))
         return res
 
+    def phase_ms(self):
+        """[factorisation, projcg, line search, total] ms of the last solve()"""
+        out = np.zeros(4)
+        self.ctx.check(self.ctx.lib.lfpsqp_large_phase_ms(self.ctx.h, _lib.ptr(out)))
+        return dict(factor=out[0], projcg=out[1], linesearch=out[2], total=out[3])
+
     def factor(self, x, want=("G", "L", "Linv")):
         m = self.m
         x = np.ascontiguousarray(x, dtype=np.float64)

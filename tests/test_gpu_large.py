@@ -167,5 +167,7 @@ def test_exact_linesearch_large_vs_oracle(L, oracle):
     with oracle.variant("fma"):   # rounding sensitivity of the golden-section decisions: oracle vs oracle(+fma)
         fx, fobj, _, ft, _ = oracle.optimize("diagquad", n, m, 0, x0, fam_params=fam.params, params=oracle.default_params(linesearch=1))
     assert status == 0 and int(info.condition) == ot["condition"] and abs(info.iter - ot["iter"]) <= 1
-    assert rel(x, ox) <= max(1e-8, 10 * rel(fx, ox))
-    assert abs(obj[-1] - oobj[-1]) <= max(1e-10, 10 * abs(fobj[-1] - oobj[-1]) / abs(oobj[-1])) * abs(oobj[-1])
+    # the golden section stops at (alpha_c - alpha_b) <= 1e-6 |d| (linesearch.jl:270) and branches on f_b < f_c between
+    # nearly equal values: an iterate is only defined to that resolution, whatever the summation order of f
+    assert rel(x, ox) <= max(1e-6, 10 * rel(fx, ox))
+    assert abs(obj[-1] - oobj[-1]) <= max(1e-8, 10 * abs(fobj[-1] - oobj[-1]) / abs(oobj[-1])) * abs(oobj[-1])
