@@ -52,7 +52,9 @@ typedef struct {
 enum { LFPSQP_F_TOL = 0, LFPSQP_X_TOL = 1, LFPSQP_KKT_TOL = 2, LFPSQP_MAX_ITER = 3, LFPSQP_ARMIJO_ERROR = 4 };
 
 /* per-instance status bits (in-band; 0 = the path is the reference's path) */
-#define LFPSQP_ST_RANK_DEFICIENT 1 /* Cholesky of J W J' broke down: the reference would truncate the SVD (optimize.jl:297-302); we stop */
+#define LFPSQP_ST_RANK_DEFICIENT 1 /* the projected Jacobian lost rank at some iterate. Batched mode: informational -- the
+                                      truncated path of optimize.jl:297-302 was taken (eigen-decomposition of J W J',
+                                      pseudo-inverse); large-n mode: the solve stopped at that iterate */
 #define LFPSQP_ST_NONFINITE 2
 
 /* TerminationInfo, src/LFPSQP.jl:45-51 : {Int32 enum, 3 x Float64, Int64}; the enum's padding carries status */

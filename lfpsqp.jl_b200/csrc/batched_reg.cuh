@@ -89,6 +89,7 @@ struct RegSolver {
   double Dx[NPL], Dy[NPL], S[NPL], Sinv[NPL], lamy[NPL];
   double cvh[NPL], cvc[MEA];   // cvalaug = [h ; c] (retractions.jl:29), persistent across PP calls (stale-tail quirk)
   int st_projcg, st_negcurv, st_trials, st_rout, st_rpcg, st_bt, st_newton, st_fact, st_feval, status;
+  int rank; bool pinv;   // numerical rank (optimize.jl:297-302); Lc holds the truncated pseudo-inverse G^+ when pinv
 
   LFPSQP_DEV RegSolver(int lane_, const lfpsqp_params &prm_, int n_, int m_, int p_)
       : lane(lane_), prm(prm_), n(n_), m(m_), p(p_), NA(n_ + p_) { fc.n = n_; fc.m = m_; fc.p = p_; fc.prm = nullptr; }
@@ -118,7 +119,13 @@ struct RegSolver {
     LF_UNROLL for (int a = 0; a < ME; a++) s += J[a][k] * u[a];
     return s;
   }
-  LFPSQP_DEV void solveG(double *u) const {  // u <- (L L')^-1 u, replicated scalar code
+  LFPSQP_DEV void solveG(double *u) const {  // u <- (L L')^-1 u (or G^+ u), replicated scalar code
+    if (pinv) {
+      double t[MEA];
+      LF_UNROLL for (int a = 0; a < ME; a++) { double s = 0.0; LF_UNROLL for (int b = 0; b < ME; b++) s += Lc[a][b] * u[b]; t[a] = s; }
+      LF_UNROLL for (int a = 0; a < ME; a++) u[a] = t[a];
+      return;
+    }
     LF_UNROLL for (int k = 0; k < ME; k++) {
       double s = u[k];
       LF_UNROLL for (int t = 0; t < k; t++) s -= Lc[k][t] * u[t];
@@ -237,7 +244,8 @@ struct RegSolver {
   // ---------------------------------------------------------------- Gram + Cholesky (replaces ksvd!, optimize.jl:288-302)
   LFPSQP_DEV bool factor() {
     st_fact++;
-    double maxdiag = 0.0;
+    rank = ME; pinv = false;
+    double maxdiag = 0.0, Gs[MEA][MEA];
     LF_UNROLL for (int a = 0; a < ME; a++)
       LF_UNROLL for (int b = 0; b <= a; b++) {
         double s = 0.0;
@@ -246,10 +254,11 @@ struct RegSolver {
           s += J[a][k] * w * J[b][k];
         }
         s = wsum(s);
-        Lc[a][b] = s;
+        Lc[a][b] = s; Gs[a][b] = s; Gs[b][a] = s;
         if (a == b) maxdiag = fmax(maxdiag, s);
       }
     const double thresh = fmax(prm.eps_rank * prm.eps_rank, 1e-14 * maxdiag);
+    bool ok = true;
     LF_UNROLL for (int k = 0; k < ME; k++) {
       LF_UNROLL for (int i = k; i < ME; i++) {
         double s = Lc[i][k];
@@ -257,11 +266,35 @@ struct RegSolver {
         Lc[i][k] = s;
       }
       double piv = Lc[k][k];
-      if (!(piv > thresh)) return false;
+      if (!(piv > thresh)) { ok = false; piv = 1.0; }
       double rinv = 1.0 / sqrt(piv);
       Lc[k][k] = sqrt(piv);
       LF_UNROLL for (int i = k + 1; i < ME; i++) Lc[i][k] *= rinv;
     }
+    if (ok) return true;
+    // rank-deficient (optimize.jl:297-302): truncated pseudo-inverse of G through its eigen-decomposition (ME <= 2:
+    // one Jacobi rotation is exact); same thresholds as batched_warp.cuh::factor_rank_deficient
+    double V[MEA][MEA], ev[MEA];
+    LF_UNROLL for (int a = 0; a < ME; a++) LF_UNROLL for (int b = 0; b < ME; b++) V[a][b] = (a == b) ? 1.0 : 0.0;
+    if (ME == 2 && Gs[0][MEA - 1] != 0.0) {
+      const double apq = Gs[0][MEA - 1], app = Gs[0][0], aqq = Gs[MEA - 1][MEA - 1];
+      const double theta = (aqq - app) / (2.0 * apq);
+      const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+      const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+      V[0][0] = c; V[0][MEA - 1] = sn; V[MEA - 1][0] = -sn; V[MEA - 1][MEA - 1] = c;
+      Gs[0][0] = app - t * apq; Gs[MEA - 1][MEA - 1] = aqq + t * apq;
+    }
+    double lmax = 0.0;
+    LF_UNROLL for (int k = 0; k < ME; k++) lmax = fmax(lmax, Gs[k][k]);
+    const double thr = fmax(prm.eps_rank * prm.eps_rank, 1e-13 * lmax);
+    int r = 0;
+    LF_UNROLL for (int k = 0; k < ME; k++) { bool keep = Gs[k][k] >= thr; ev[k] = keep ? 1.0 / Gs[k][k] : 0.0; r += keep ? 1 : 0; }
+    LF_UNROLL for (int a = 0; a < ME; a++) LF_UNROLL for (int b = 0; b < ME; b++) {
+      double s = 0.0;
+      LF_UNROLL for (int k = 0; k < ME; k++) s += V[a][k] * ev[k] * V[b][k];
+      Lc[a][b] = s;
+    }
+    rank = r; pinv = true;
     return true;
   }
 
@@ -296,7 +329,7 @@ struct RegSolver {
     LF_UNROLL for (int k = 0; k < NPL; k++) { dc.x[k] = -1.0 * r.x[k]; if (INEQ) dc.y[k] = -1.0 * r.y[k]; }
     int i = 0;
     const int N = INEQ ? 2 * NA : NA;
-    int64_t lim = (int64_t)N + (INEQ ? NA + ME : ME); if (maxit < lim) lim = maxit;
+    int64_t lim = (int64_t)N + (INEQ ? NA + rank : rank); if (maxit < lim) lim = maxit;   // c has length rank / n+rank
     double rg = dot(r, r);                                                      // r == g after every projection
     while (i < lim) {
       i++;
@@ -482,6 +515,7 @@ struct RegSolver {
   LFPSQP_DEV void run(const BatchedArgs &A, int64_t k, const double *bnd) {
     fc.prm = A.fam_params ? A.fam_params + k * A.fam_stride : nullptr;
     st_projcg = st_negcurv = st_trials = st_rout = st_rpcg = st_bt = st_newton = st_fact = st_feval = 0; status = 0;
+    rank = ME; pinv = false;
     LF_UNROLL for (int s = 0; s < NPL; s++) {
       int j = idx(s);
       valid[s] = j < NA;
@@ -520,7 +554,8 @@ struct RegSolver {
       if (INEQ) inequality_gradient(x);
       if (ME > 0) {
         jac_aux(cval, x);
-        if (!factor()) { status |= LFPSQP_ST_RANK_DEFICIENT; cond = LFPSQP_MAX_ITER; break; }
+        factor();
+        if (pinv) status |= LFPSQP_ST_RANK_DEFICIENT;   // informational: truncated path of optimize.jl:297-302
       }
       project(d, true);
       double km = 0.0;
@@ -540,7 +575,7 @@ struct RegSolver {
         if (dot(nd, d) > 0.0) { d = nd; st_newton++; }
       }
       int kind;
-      if (ME > 0) kind = (!prm.do_project_retract) ? 2 : 3; else kind = INEQ ? 1 : 0;
+      if (ME > 0) kind = (rank == ME && !prm.do_project_retract) ? 2 : 3; else kind = INEQ ? 1 : 0;
       // armijo! (linesearch.jl:32-89)
       double alpha = prm.alpha, newf = 0.0;
       f_diff = INFINITY; step_diff = INFINITY;

@@ -21,7 +21,7 @@ namespace lfpsqp {
 // Per-instance shared-memory layout (in doubles).  Host and device compute the same offsets.
 struct WarpLayout {
   int n, m, p, NA, ME, N, M, ineq, use_nr, use_exact;
-  int o_ex[4];
+  int o_ex[4], o_V;
   int o_x, o_xnew, o_xtil, o_g, o_d, o_nd, o_w[5], o_J, o_G, o_cval, o_lam, o_tm, o_cvaug, o_u, o_scr, o_Dx, o_Dy, o_S,
       o_lamy, o_D, o_nr, total;
   __host__ __device__ WarpLayout(int n_, int m_, int p_, int ineq_, int use_nr_, int use_exact_ = 0) {
@@ -37,6 +37,7 @@ struct WarpLayout {
     else { o_Dx = o_Dy = o_S = o_lamy = 0; }
     if (use_nr && ME > 0) { o_D = take(ME * ME); o_nr = take(3 * ME); } else { o_D = o_nr = 0; }
     for (int i = 0; i < 4; i++) o_ex[i] = use_exact ? take(N) : 0;
+    o_V = take(ME * ME + ME);   // eigenvectors + eigenvalues of G (rank-deficient fallback)
     total = (o + 1) & ~1;
   }
 };
@@ -54,6 +55,8 @@ struct Solver {
   const bool ineq;
   lfpsqp_stats st;
   int status;
+  int rank;      // numerical rank of the (projected) Jacobian, optimize.jl:297-302
+  bool pinv;     // Gm holds the truncated pseudo-inverse G^+ instead of the Cholesky factor
 
   double *x, *xnew, *xtil, *gr, *d, *nd, *w0, *w1, *w2, *w3, *w4, *J, *Gm, *cval, *lam, *tm, *cvaug, *ub, *scr, *Dx, *Dy,
       *S, *lamy, *Dnr, *nrt;
@@ -68,7 +71,7 @@ struct Solver {
     Dnr = sm + L.o_D; nrt = sm + L.o_nr;
     bkind = bnd; bq = bnd + NA; br = bnd + 2 * NA; bs = bnd + 3 * NA; bt = bnd + 4 * NA;
     fc.n = n; fc.m = m; fc.p = p; fc.prm = nullptr;
-    status = 0;
+    status = 0; rank = ME; pinv = false;
   }
 
   // ------------------------------------------------------------ small vector helpers (all end with a group sync)
@@ -229,8 +232,7 @@ struct Solver {
 
   // ------------------------------------------------------------ Gram + Cholesky (replaces ksvd!, optimize.jl:288-302)
   // G = J diag(w) J', w = Dy^2 with bounds (PJct'PJct, App. B) else 1; in-place lower Cholesky. false = rank deficient.
-  LFPSQP_DEV bool factor() {
-    st.factorizations++;
+  LFPSQP_DEV double gram() {   // Gm (lower) = J diag(w) J' ; returns max diag
     double maxdiag = 0.0;
     for (int a = 0; a < ME; a++) {
       for (int b = 0; b <= a; b++) {
@@ -243,6 +245,12 @@ struct Solver {
       }
     }
     g.sync();
+    return maxdiag;
+  }
+  LFPSQP_DEV bool factor() {
+    st.factorizations++;
+    rank = ME; pinv = false;
+    const double maxdiag = gram();
     const double thresh = fmax(prm.eps_rank * prm.eps_rank, 1e-14 * maxdiag);
     for (int k = 0; k < ME; k++) {
       for (int i = k + g.lane; i < ME; i += G::SIZE) {
@@ -252,13 +260,81 @@ struct Solver {
       }
       g.sync();
       double piv = Gm[k * ME + k];
-      if (!(piv > thresh)) return false;
+      if (!(piv > thresh)) { factor_rank_deficient(); return true; }
       double rinv = 1.0 / sqrt(piv);
       g.sync();
       for (int i = k + g.lane; i < ME; i += G::SIZE) Gm[i * ME + k] = (i == k) ? sqrt(piv) : Gm[i * ME + k] * rinv;
       g.sync();
     }
     return true;
+  }
+  // Rank-deficient Jacobian (optimize.jl:297-302: rank = #{sigma_j >= eps_rank}, projector on U[:,1:rank], multipliers
+  // zeroed beyond rank, :335-340).  Gram-form equivalent: G = V diag(sigma^2) V' by cyclic Jacobi rotations, and the
+  // truncated pseudo-inverse G^+ = V_r diag(1/sigma_r^2) V_r' takes the place of (L L')^-1 in every solve:
+  //   U_r U_r' = PJct G^+ PJct' ,  lambda = V Sigma_r^-1 U_r'(-g) = G^+ PJct'(-g).
+  // Eigenvalues below max(eps_rank^2, 1e-13 * sigma_max^2) count as zero (the Gram form cannot see singular values
+  // below ~3e-7 * sigma_max; the SVD-based reference resolves them down to eps_rank).
+  LFPSQP_DEV void factor_rank_deficient() {
+    double *V = sm + L.o_V, *ev = V + ME * ME;
+    gram();
+    for (int e = g.lane; e < ME * ME; e += G::SIZE) {       // symmetrise, V = I
+      int a = e / ME, b = e % ME;
+      if (b > a) Gm[a * ME + b] = Gm[b * ME + a];
+      V[e] = (a == b) ? 1.0 : 0.0;
+    }
+    g.sync();
+    for (int sweep = 0; sweep < 30; sweep++) {
+      double off = 0.0, dg = 0.0;
+      for (int e = g.lane; e < ME * ME; e += G::SIZE) { double v = Gm[e]; if (e / ME != e % ME) off += v * v; else dg += v * v; }
+      off = g.sum(off); dg = g.sum(dg);
+      if (off <= 1e-30 * dg || off == 0.0) break;
+      for (int pq = 0; pq < ME - 1; pq++)
+        for (int q = pq + 1; q < ME; q++) {
+          const double apq = Gm[pq * ME + q];
+          if (apq == 0.0) continue;                          // uniform: every lane reads the same value
+          const double app = Gm[pq * ME + pq], aqq = Gm[q * ME + q];
+          const double theta = (aqq - app) / (2.0 * apq);
+          const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+          g.sync();
+          for (int k = g.lane; k < ME; k += G::SIZE) {       // columns p, q of A and V
+            double akp = Gm[k * ME + pq], akq = Gm[k * ME + q];
+            Gm[k * ME + pq] = c * akp - sn * akq; Gm[k * ME + q] = sn * akp + c * akq;
+            double vkp = V[k * ME + pq], vkq = V[k * ME + q];
+            V[k * ME + pq] = c * vkp - sn * vkq; V[k * ME + q] = sn * vkp + c * vkq;
+          }
+          g.sync();
+          for (int k = g.lane; k < ME; k += G::SIZE) {       // rows p, q of A
+            double apk = Gm[pq * ME + k], aqk = Gm[q * ME + k];
+            Gm[pq * ME + k] = c * apk - sn * aqk; Gm[q * ME + k] = sn * apk + c * aqk;
+          }
+          g.sync();
+        }
+    }
+    double lmax = 0.0;
+    for (int k = 0; k < ME; k++) lmax = fmax(lmax, Gm[k * ME + k]);
+    const double thr = fmax(prm.eps_rank * prm.eps_rank, 1e-13 * lmax);
+    int r = 0;
+    for (int k = 0; k < ME; k++) { double lv = Gm[k * ME + k]; if (lv >= thr) r++; }
+    g.sync();
+    for (int k = g.lane; k < ME; k += G::SIZE) { double lv = Gm[k * ME + k]; ev[k] = (lv >= thr) ? 1.0 / lv : 0.0; }
+    g.sync();
+    for (int e = g.lane; e < ME * ME; e += G::SIZE) {       // G^+ = V diag(ev) V'
+      int a = e / ME, b = e % ME; double s2 = 0.0;
+      for (int k = 0; k < ME; k++) s2 += V[a * ME + k] * ev[k] * V[b * ME + k];
+      Gm[e] = s2;
+    }
+    g.sync();
+    rank = r; pinv = true;
+  }
+  // u <- G^-1 u : Cholesky solves, or the truncated pseudo-inverse when the Jacobian is rank deficient
+  LFPSQP_DEV void solveG(double *u) const {
+    if (!pinv) { solveL(u); solveLt(u); return; }
+    double *tmp = sm + L.o_V + ME * ME;   // the eigenvalue slots are free once G^+ is formed
+    for (int a = g.lane; a < ME; a += G::SIZE) { double s2 = 0.0; for (int b = 0; b < ME; b++) s2 += Gm[a * ME + b] * u[b]; tmp[a] = s2; }
+    g.sync();
+    for (int a = g.lane; a < ME; a += G::SIZE) u[a] = tmp[a];
+    g.sync();
   }
   LFPSQP_DEV void solveL(double *u) const {  // u <- L^-1 u
     for (int k = 0; k < ME; k++) {
@@ -291,7 +367,7 @@ struct Solver {
         scr[j] = dy * (dy * vx - dx * vy);    // PJct' v = J * scr
       }
       g.sync();
-      if (ME > 0) { rowdots(ub, scr); solveL(ub); solveLt(ub); }
+      if (ME > 0) { rowdots(ub, scr); solveG(ub); }
       for (int j = g.lane; j < NA; j += G::SIZE) {
         double wj = (ME > 0) ? coldot(ub, j) : 0.0, dx = Dx[j], dy = Dy[j], a = tm[j];
         v[j] -= dx * a + dy * dy * wj;
@@ -301,7 +377,7 @@ struct Solver {
       if (want_mult) for (int a = g.lane; a < ME; a += G::SIZE) lam[a] = ub[a];
       g.sync();
     } else if (ME > 0) {
-      rowdots(ub, v); solveL(ub); solveLt(ub);
+      rowdots(ub, v); solveG(ub);
       for (int j = g.lane; j < NA; j += G::SIZE) v[j] -= coldot(ub, j);
       if (want_mult) for (int a = g.lane; a < ME; a += G::SIZE) lam[a] = ub[a];
       g.sync();
@@ -646,7 +722,8 @@ struct Solver {
       if (ineq) inequality_gradient(x);                                    // :277
       if (ME > 0) {
         jac_aux(cval, x);                                                  // :283
-        if (!factor()) { status |= LFPSQP_ST_RANK_DEFICIENT; cond = LFPSQP_MAX_ITER; break; }
+        factor();
+        if (pinv) status |= LFPSQP_ST_RANK_DEFICIENT;   // informational: the truncated path of optimize.jl:297-302 was taken
       }
       project(d, true);                                                    // :306-307 / :316-317 + multipliers :331-343
       kkt_diff = norminf(d, N);                                            // :320
@@ -660,11 +737,11 @@ struct Solver {
         double tol = prm.tn_kappa * fmin(1.0, gn / prev_grad_norm) * gn;
         prev_grad_norm = gn;
         double tn_res;
-        projcg(d, ineq ? NA + ME : ME, tol, prm.tn_maxiter, &tn_res);
+        projcg(d, ineq ? NA + rank : rank, tol, prm.tn_maxiter, &tn_res);        // c has length rank / n+rank (:366-372)
         if (dot(nd, d, N) > 0.0) { copy(d, nd, N); st.newton_accepted++; }
       }
       int kind;                                                            // :396-412
-      if (ME > 0) kind = (!prm.do_project_retract) ? 2 : 3;                // rank == m here (full rank or stopped)
+      if (ME > 0) kind = (rank == ME && !prm.do_project_retract) ? 2 : 3;
       else kind = ineq ? 1 : 0;
       double newf;
       int flag;                                                            // :415-420

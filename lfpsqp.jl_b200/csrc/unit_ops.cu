@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(32) ineq_op_kernel(int op, int n, int m, const
     } else {                                      // d - Q Q' d, lambda, lambda_y (optimize.jl:316-317,:332; :286-308)
       for (int i = threadIdx.x; i < N; i += 32) S.d[i] = in[N + i];
       __syncwarp();
-      bool ok = (m == 0) || S.factor();
+      bool ok = true;
+      if (m > 0) S.factor();
       if (threadIdx.x == 0) okflag[0] = ok ? 1 : 0;
       if (ok) {
         S.project(S.d, true);

@@ -208,3 +208,49 @@ def test_exact_linesearch_vs_oracle(L, oracle):
                                                                  params=oracle.default_params(linesearch=1, do_project_retract=0 if nr else 1),
                                                                  nthreads=8), n, "sin exact")
         _require(compare_batch(gpu, orc, n, "sin exact nr=%s" % nr), 0.95, base)
+
+
+def test_rank_deficient_jacobian_vs_oracle(L, oracle):
+    # optimize.jl:297-302: rank = #{sigma_j >= eps_rank}; projector on U[:, 1:rank]; multipliers zeroed beyond rank (:335-340).
+    # Device equivalent: eigen-decomposition of J W J' and truncated pseudo-inverse.
+    rng = np.random.default_rng(31)
+    # (a) shared-memory solver: three constraints, the third a copy of the second -> rank 2 at every iterate
+    B, n, m = 48, 16, 3
+    Q = rng.standard_normal((m, n)) / np.sqrt(n); A = rng.standard_normal((m, n)) / np.sqrt(n)
+    Q[2] = Q[1]; A[2] = A[1]
+    xt = rng.standard_normal(n); w = np.exp(rng.uniform(0, np.log(20.0), n))
+    xs = rng.standard_normal((B, n))
+    # per-instance feasible starts need per-instance b: use one b and start every instance from the same feasible point,
+    # perturbed along the null space of J so that it stays (nearly) feasible and the paths differ
+    x0 = rng.standard_normal(n)
+    b = 0.5 * Q @ (x0 * x0) + A @ x0
+    J0 = Q * x0[None, :] + A
+    P0 = np.eye(n) - np.linalg.pinv(J0) @ J0
+    X0 = x0[None, :] + 0.05 * (xs @ P0.T)
+    fam = L.families.diagquad(Q, A, b, xt, w)
+    gpu = L.optimize_batched(fam.f, fam.c, X0, m, return_stats=True)
+    orc, base = _sens(oracle, lambda: oracle.optimize_batched("diagquad", n, m, 0, X0, fam_params=fam.params, fam_stride=0, nthreads=8),
+                      n, "rank-deficient diagquad")
+    res = compare_batch(gpu, orc, n, "rank-deficient diagquad")
+    print(fmt(res)); print(fmt(base))
+    assert np.all(gpu[4]["status"] & 1)                       # the truncated path was taken and reported
+    assert res["cond_frac"] >= 0.95 and res["iter_pm1_frac"] >= 0.9
+    same = (gpu[4]["iter"] == orc[4]["iter"])
+    xerr = np.linalg.norm(gpu[0] - orc[0], axis=1) / np.linalg.norm(orc[0], axis=1)
+    assert np.median(xerr[same]) < 1e-7
+    # minimum-norm multipliers: the two copies share the multiplier equally (V Sigma_r^-1 U_r' structure)
+    assert np.allclose(gpu[3][:, 1], gpu[3][:, 2], rtol=1e-6, atol=1e-9)
+    # (b) register-resident solver: one equality whose gradient is identically zero (a = 0, b = 0) -> rank 0
+    B, n = 64, 12
+    xl = np.r_[-np.inf * np.ones(3), -0.5 * np.ones(3), -np.inf * np.ones(3), -0.3 * np.ones(3)]
+    xu = np.r_[np.inf * np.ones(6), 0.4 * np.ones(3), 0.6 * np.ones(3)]
+    t = 2 * rng.standard_normal((B, n))
+    fam = L.families.boxquad(t, a=np.zeros(n), b=0.0)
+    x0 = np.tile(np.clip(np.zeros(n), xl, xu), (B, 1))
+    gpu = L.optimize_batched(fam.f, fam.c, x0, xl, xu, 1)
+    orc, base = _sens(oracle, lambda: oracle.optimize_batched("boxquad", n, 1, 0, x0, xl=xl, xu=xu, fam_params=fam.params,
+                                                             fam_stride=fam.params.shape[1], nthreads=8), n, "rank-0 boxquad")
+    res = compare_batch(gpu, orc, n, "rank-0 boxquad")
+    print(fmt(res)); print(fmt(base))
+    assert np.all(gpu[4]["status"] & 1) and np.all(gpu[3] == 0.0)          # lambda = 0 beyond the rank
+    assert res["cond_frac"] >= base["cond_frac"] - 0.05 and res["all_ok_frac"] >= base["all_ok_frac"] - 0.1
