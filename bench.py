@@ -114,15 +114,15 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def large_n_section(L, ctx, torch, dev, with_cpu, dist=None, rank=0, world=1):
+def large_n_section(L, ctx, torch, dev, with_cpu, dist=None, rank=0, world=1, weak=False):
     """Secondary metric of BASELINE.json: large-n projcg iterations/s on config C5 (n=65536, m=2048 dense random
     diagonal-quadratic equality constraints, definition pinned in DESIGN.md), fixed-K projcg (tol=0) through the
     unit-level export, plus the FP64 DMMA Gram.  Inputs are generated on the device (2 GB of parameters).
     With world > 1 the instance is column-sharded (strong scaling): NCCL all-reduces the Gram, J v and the CG scalars."""
     from lfpsqp.jl_b200 import dist as D
-    n, m, K = 65536, 2048, 64
+    n, m, K = 65536 * (world if weak else 1), 2048, 64
     col0, nloc = D.column_range(n, world, rank)
-    if world > 1:
+    if world > 1 and ctx.lib.lfpsqp_comm_mode(ctx.h) == 0:
         D.init_comm(ctx, dist)
     g = torch.Generator(device=dev); g.manual_seed(SEED)     # same stream on every rank; each keeps its column shard
 
@@ -173,7 +173,8 @@ def large_n_section(L, ctx, torch, dev, with_cpu, dist=None, rank=0, world=1):
     out = {"metric": "large-n projcg iterations/s", "value": 1e3 / ms_it, "unit": "iterations/s",
            "config": {"workload": "C5 large dense: n=65536, m=2048, c_i = 1/2 sum_j Q_ij x_j^2 + A_i.x - b_i, "
                                   "f = 1/2 (x-xt)' diag(w) (x-xt), fixed K=%d projcg iterations (tol=0), column-sharded over %d GPU(s)" % (K, world),
-                      "scaling": "strong (total work fixed, J and x sharded by columns)",
+                      "scaling": ("weak (n = 65536 per GPU, m fixed)" if weak else "strong (total work fixed, J and x sharded by columns)"),
+                      "n": n, "comm": {0: "none", 1: "NCCL", 2: "peer-memory all-reduce kernels (CUDA IPC over NVLink) + NCCL for the Gram"}[ctx.lib.lfpsqp_comm_mode(ctx.h)],
                       "l2": "J alone is 1 GiB per pass (>> 126 MB L2)"},
            "ms_per_iteration": ms_it, "gpu_launches_per_iteration": launches / K,
            "roofline": {"bound": "hbm", "kernels": "rows_dot_kernel + cols_dot_kernel (+ tri_gemv, cg_update*)",
@@ -476,6 +477,8 @@ def main():
         try:
             line["large_n"] = large_n_section(L, ctx, torch, dev, (not args.no_cpu_baseline) and world == 1 and rank == 0,
                                               dist, rank, world)
+            if world > 1:
+                line["large_n_weak"] = large_n_section(L, ctx, torch, dev, False, dist, rank, world, weak=True)
         except Exception as e:  # noqa
             line["large_n"] = {"error": repr(e)}
     if world == 1 and not args.skip_large:

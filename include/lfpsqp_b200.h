@@ -180,6 +180,13 @@ int lfpsqp_ineq_op(lfpsqp_ctx *ctx, int op, int64_t n, int64_t m, const double *
 int lfpsqp_comm_unique_id(void *out128, const char *nccl_lib_path);
 int lfpsqp_comm_init(lfpsqp_ctx *ctx, int rank, int world, const void *unique_id128, const char *nccl_lib_path);
 int lfpsqp_comm_destroy(lfpsqp_ctx *ctx);
+/* Peer-memory all-reduce for the small latency-bound messages of the large-n path (m-vectors, packed CG scalars): one
+ * kernel per all-reduce that stores flags / loads partial sums directly in the peers' memory over NVLink (CUDA IPC),
+ * summing in rank order (bitwise-identical result on every rank).  Each rank exports a 64-byte handle, the host
+ * program all-gathers them (rank order) and every rank imports.  Without it NCCL carries these messages too. */
+int lfpsqp_comm_ipc_export(lfpsqp_ctx *ctx, void *handle64_out);
+int lfpsqp_comm_ipc_import(lfpsqp_ctx *ctx, const void *handles /* world x 64 bytes */);
+int lfpsqp_comm_mode(lfpsqp_ctx *ctx); /* 0 single GPU, 1 NCCL only, 2 peer-memory kernels + NCCL (Gram) */
 
 /* Roofline denominators that MEASURED_PEAKS.json does not carry: measured FP64 peak of this GPU in TFLOP/s.
  * which: 0 = DFMA (vector pipe), 1 = DMMA (mma.sync.m8n8k4.f64 tensor pipe). */

@@ -32,7 +32,7 @@ EXPORTS = [
     "lfpsqp_solve_batched_dev", "lfpsqp_bench_fp64_peak", "lfpsqp_solve_large", "lfpsqp_large_setup",
     "lfpsqp_large_solve", "lfpsqp_large_factor", "lfpsqp_large_project", "lfpsqp_large_projcg",
     "lfpsqp_comm_unique_id", "lfpsqp_comm_init", "lfpsqp_comm_destroy", "lfpsqp_large_retract", "lfpsqp_large_pcg",
-    "lfpsqp_ineq_op", "lfpsqp_large_phase_ms",
+    "lfpsqp_ineq_op", "lfpsqp_large_phase_ms", "lfpsqp_comm_ipc_export", "lfpsqp_comm_ipc_import", "lfpsqp_comm_mode",
 ]
 
 _lib = None
@@ -75,6 +75,9 @@ def load():
         lib.lfpsqp_large_pcg.argtypes = [P, P, C.c_double, P, C.c_double, I, P, P, P, P]
         lib.lfpsqp_ineq_op.argtypes = [P, C.c_int, I, I, P, P, P, P, I, P, I]
         lib.lfpsqp_large_phase_ms.argtypes = [P, P]
+        lib.lfpsqp_comm_ipc_export.argtypes = [P, P]
+        lib.lfpsqp_comm_ipc_import.argtypes = [P, P]
+        lib.lfpsqp_comm_mode.argtypes = [P]
         _lib = lib
     return _lib
 

@@ -9,6 +9,7 @@
 
 #include "ctx.h"
 #include "large_state.h"
+#include "large_device.cuh"
 
 using namespace lfpsqp;
 
@@ -85,12 +86,113 @@ void ar(LargeState &S, double *buf, size_t count, int op) {
   if (r != 0) fprintf(stderr, "lfpsqp: ncclAllReduce failed: %s\n", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
   S.collectives++;
 }
+
+// ------------------------------------------------------------------ peer-memory all-reduce (one kernel, no NCCL)
+// Region layout per rank (doubles): data[2][PC_MAX + PC_SCAL] then flags[PC_RANKS][PC_COLS] (unsigned long long).
+// Protocol per call (epoch e, parity e&1): every CTA (1) writes its slice of the local contribution into its OWN
+// region, (2) __threadfence_system, (3) stores e into flags[my_rank][cta] of EVERY peer's region (remote stores over
+// NVLink), (4) spins until flags[r][cta] >= e for all r in its own region, (5) sums the slices of all ranks in rank
+// order through the mapped peer pointers (remote loads) -- the same order everywhere, so every rank gets the
+// bitwise-identical result.  A region is reused two calls later; a peer's flag for call e+1 implies that its reads of
+// call e are complete (stream order), so the parity double buffer is race-free.
+constexpr int PC_MAX = 8192, PC_SCAL = 32, PC_RANKS = 8, PC_COLS = 16;
+constexpr size_t PC_DATA = 2 * (size_t)(PC_MAX + PC_SCAL);
+constexpr size_t PC_REGION_BYTES = PC_DATA * 8 + (size_t)PC_RANKS * PC_COLS * 8;
+
+struct PeerPtrs { double *r[PC_RANKS]; };
+
+__device__ __forceinline__ unsigned long long *pc_flags(double *region) { return reinterpret_cast<unsigned long long *>(region + PC_DATA); }
+__device__ __forceinline__ double ld_sys(const double *p) { double v; asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; }
+
+__device__ __forceinline__ bool pc_exchange(const PeerPtrs &P, int rank, int world, unsigned long long epoch, int col, LargeCtrl *ctrl) {
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < world) {
+    unsigned long long *f = pc_flags(P.r[threadIdx.x]) + (size_t)rank * PC_COLS + col;   // my flag slot in peer threadIdx.x
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+  }
+  bool ok = true;
+  if ((int)threadIdx.x < world) {
+    const unsigned long long *f = pc_flags(P.r[rank]) + (size_t)threadIdx.x * PC_COLS + col;  // peer's flag in MY region
+    long long t0 = clock64();
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+      if (v >= epoch) break;
+      if (clock64() - t0 > 4000000000LL) { ok = false; ctrl->rankflag = 99; break; }   // ~2 s: a peer died; do not hang the GPU
+    } while (true);
+  }
+  __syncthreads();
+  return ok;
+}
+
+// vector flavour: dst[i] = sum_r src_r[i], i < count <= PC_MAX ; CTA c handles [c*1024, c*1024+1024)
+__global__ void __launch_bounds__(256) peer_allreduce_vec_kernel(PeerPtrs P, int rank, int world, unsigned long long epoch,
+                                                                 const double *src, double *dst, int count, LargeCtrl *ctrl) {
+  const int par = (int)(epoch & 1), base = blockIdx.x * 1024;
+  double *mine = P.r[rank] + (size_t)par * (PC_MAX + PC_SCAL);
+  for (int i = base + threadIdx.x; i < min(count, base + 1024); i += 256) mine[i] = src[i];
+  pc_exchange(P, rank, world, epoch, blockIdx.x, ctrl);
+  for (int i = base + threadIdx.x; i < min(count, base + 1024); i += 256) {
+    double s = 0.0;
+    for (int r = 0; r < world; r++) s += ld_sys(P.r[r] + (size_t)par * (PC_MAX + PC_SCAL) + i);
+    dst[i] = s;
+  }
+}
+
+// scalar flavour (one CTA): for every masked slot k: v_k = reduce(part[k][0..np)) locally (sum or max), all-reduced,
+// and written back to part[k][0] (consumers then read np = 1) and, if ctrl_out, to ctrl->s[k].
+// from_ctrl: take the local value from ctrl->s[k] instead of reducing partials.
+__global__ void __launch_bounds__(256) peer_allreduce_slots_kernel(PeerPtrs P, int rank, int world, unsigned long long epoch,
+                                                                   double *part, int np, unsigned mask, int domax, int from_ctrl,
+                                                                   int ctrl_out, LargeCtrl *ctrl) {
+  __shared__ double sh[33];
+  const int par = (int)(epoch & 1);
+  double *mine = P.r[rank] + (size_t)par * (PC_MAX + PC_SCAL) + PC_MAX;
+  for (int k = 0; k < 16; k++) {
+    if (!(mask & (1u << k))) continue;
+    double r;
+    if (from_ctrl) r = ctrl->s[k];
+    else r = domax ? reduce_partials_max(part + (size_t)k * MAXP, np, sh) : reduce_partials(part + (size_t)k * MAXP, np, sh);
+    if (threadIdx.x == 0) mine[k] = r;
+    __syncthreads();
+  }
+  pc_exchange(P, rank, world, epoch, PC_COLS - 1, ctrl);
+  if (threadIdx.x < 16 && (mask & (1u << threadIdx.x))) {
+    const int k = threadIdx.x;
+    double s = domax ? 0.0 : 0.0;
+    for (int r = 0; r < world; r++) {
+      double v = ld_sys(P.r[r] + (size_t)par * (PC_MAX + PC_SCAL) + PC_MAX + k);
+      s = domax ? ((v > s || isnan(v)) ? v : s) : s + v;
+    }
+    if (!from_ctrl) part[(size_t)k * MAXP] = s;
+    if (ctrl_out || from_ctrl) ctrl->s[k] = s;
+  }
+}
+
+PeerPtrs peer_ptrs(LargeState &S) { PeerPtrs P; for (int r = 0; r < PC_RANKS; r++) P.r[r] = S.comm->peer_map[r]; return P; }
+bool use_peer(LargeState &S, size_t count) { return S.comm && S.comm->peer_ready && count <= (size_t)PC_MAX; }
 }  // namespace
 
-void comm_allreduce(LargeState &S, double *buf, size_t count) { ar(S, buf, count, ncclSum); }
+void comm_allreduce(LargeState &S, double *buf, size_t count) {
+  if (S.world <= 1) return;
+  if (use_peer(S, count)) {
+    unsigned long long e = ++S.comm->epoch;
+    peer_allreduce_vec_kernel<<<(unsigned)((count + 1023) / 1024), 256, 0, S.stream>>>(peer_ptrs(S), S.rank, S.world, e, buf, buf, (int)count, S.ctrl);
+    S.launches++; S.collectives++;
+    return;
+  }
+  ar(S, buf, count, ncclSum);
+}
 
 void comm_allreduce_scalars(LargeState &S, unsigned summask, unsigned maxmask) {
   if (S.world <= 1) return;
+  if (use_peer(S, 1)) {
+    if (summask) { unsigned long long e = ++S.comm->epoch; peer_allreduce_slots_kernel<<<1, 256, 0, S.stream>>>(peer_ptrs(S), S.rank, S.world, e, nullptr, 0, summask, 0, 1, 1, S.ctrl); }
+    if (maxmask) { unsigned long long e = ++S.comm->epoch; peer_allreduce_slots_kernel<<<1, 256, 0, S.stream>>>(peer_ptrs(S), S.rank, S.world, e, nullptr, 0, maxmask, 1, 1, 1, S.ctrl); }
+    S.launches += 2; S.collectives += 2;
+    return;
+  }
   if (summask) {
     pack_scalars_kernel<<<1, 1, 0, S.stream>>>(S.ctrl, summask, S.commbuf);
     ar(S, S.commbuf, __builtin_popcount(summask), ncclSum);
@@ -104,24 +206,67 @@ void comm_allreduce_scalars(LargeState &S, unsigned summask, unsigned maxmask) {
   S.launches += 4;
 }
 
-void comm_allreduce_loop_slot(LargeState &S, int slot, int np) {
-  if (S.world <= 1) return;
-  pack_slots_kernel<<<1, 256, 0, S.stream>>>(S.lp, np, 1u << slot, 0, S.commbuf + 32);
-  ar(S, S.commbuf + 32, 1, ncclSum);
-  unpack_slots_kernel<<<1, 1, 0, S.stream>>>(S.lp, 1u << slot, S.commbuf + 32);
+static void slots_allreduce(LargeState &S, unsigned mask, int np) {
+  if (use_peer(S, 1)) {
+    unsigned long long e = ++S.comm->epoch;
+    peer_allreduce_slots_kernel<<<1, 256, 0, S.stream>>>(peer_ptrs(S), S.rank, S.world, e, S.lp, np, mask, 0, 0, 0, S.ctrl);
+    S.launches++; S.collectives++;
+    return;
+  }
+  pack_slots_kernel<<<1, 256, 0, S.stream>>>(S.lp, np, mask, 0, S.commbuf + 32);
+  ar(S, S.commbuf + 32, __builtin_popcount(mask), ncclSum);
+  unpack_slots_kernel<<<1, 1, 0, S.stream>>>(S.lp, mask, S.commbuf + 32);
   S.launches += 2;
 }
-
+void comm_allreduce_loop_slot(LargeState &S, int slot, int np) {
+  if (S.world <= 1) return;
+  slots_allreduce(S, 1u << slot, np);
+}
 void comm_allreduce_loop_slots_cg(LargeState &S, int par) {
   if (S.world <= 1) return;
-  unsigned mask = (1u << 1) | (1u << (2 + par));
-  pack_slots_kernel<<<1, 256, 0, S.stream>>>(S.lp, S.np_loop_raw, mask, 0, S.commbuf + 40);
-  ar(S, S.commbuf + 40, 2, ncclSum);
-  unpack_slots_kernel<<<1, 1, 0, S.stream>>>(S.lp, mask, S.commbuf + 40);
-  S.launches += 2;
+  slots_allreduce(S, (1u << 1) | (1u << (2 + par)), S.np_loop_raw);
 }
 
 void comm_release(LargeState &) {}
+
+// ---- CUDA IPC plumbing of the peer-memory all-reduce: every rank exports one region, maps everybody else's
+extern "C" int lfpsqp_comm_ipc_export(lfpsqp_ctx *c, void *handle64_out) {
+  if (!c || !handle64_out) return LFPSQP_ERR_ARG;
+  cudaSetDevice(c->device);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!c->comm.peer_local) {
+    if (cudaMalloc((void **)&c->comm.peer_local, PC_REGION_BYTES) != cudaSuccess) { cudaGetLastError(); return c->fail(LFPSQP_ERR_NOMEM, "peer region allocation failed"); }
+    cudaMemset(c->comm.peer_local, 0, PC_REGION_BYTES);
+    cudaDeviceSynchronize();
+  }
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, c->comm.peer_local);
+  if (e != cudaSuccess) return c->cuda_fail(e, "cudaIpcGetMemHandle");
+  memcpy(handle64_out, &h, 64);
+  return LFPSQP_OK;
+}
+// handles: world x 64 bytes, in rank order.  Call after every rank exported and after lfpsqp_comm_init.
+extern "C" int lfpsqp_comm_ipc_import(lfpsqp_ctx *c, const void *handles) {
+  if (!c || !handles) return LFPSQP_ERR_ARG;
+  if (c->comm.world < 2 || c->comm.world > PC_RANKS || !c->comm.peer_local) return c->fail(LFPSQP_ERR_ARG, "peer all-reduce needs 2..8 ranks and an exported region");
+  cudaSetDevice(c->device);
+  for (int r = 0; r < c->comm.world; r++) {
+    if (r == c->comm.rank) { c->comm.peer_map[r] = c->comm.peer_local; continue; }
+    cudaIpcMemHandle_t h; memcpy(&h, (const char *)handles + 64 * r, 64);
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { c->comm.peer_ready = false; return c->cuda_fail(e, "cudaIpcOpenMemHandle (peer-memory all-reduce unavailable; NCCL is used instead)"); }
+    c->comm.peer_map[r] = (double *)p;
+  }
+  c->comm.epoch = 0;
+  c->comm.peer_ready = true;
+  return LFPSQP_OK;
+}
+// 0 = single GPU, 1 = NCCL only, 2 = peer-memory kernels for small messages + NCCL for the Gram
+extern "C" int lfpsqp_comm_mode(lfpsqp_ctx *c) {
+  if (!c || c->comm.world <= 1) return 0;
+  return c->comm.peer_ready ? 2 : 1;
+}
 
 extern "C" int lfpsqp_comm_unique_id(void *out128, const char *nccl_lib_path) {
   std::string err;
@@ -148,6 +293,9 @@ extern "C" int lfpsqp_comm_init(lfpsqp_ctx *c, int rank, int world, const void *
 
 extern "C" int lfpsqp_comm_destroy(lfpsqp_ctx *c) {
   if (!c) return LFPSQP_ERR_ARG;
+  cudaSetDevice(c->device);
+  for (int r = 0; r < 8; r++) if (c->comm.peer_map[r] && c->comm.peer_map[r] != c->comm.peer_local) cudaIpcCloseMemHandle(c->comm.peer_map[r]);
+  if (c->comm.peer_local) cudaFree(c->comm.peer_local);
   if (c->comm.nccl && g_nccl.CommDestroy) { cudaSetDevice(c->device); g_nccl.CommDestroy((ncclComm_t)c->comm.nccl); }
   c->comm = CommState();
   return LFPSQP_OK;

@@ -9,9 +9,15 @@
 
 struct LargeState;  // large-n mode workspace (large.cu)
 
-struct CommState {           // NCCL communicator of a column-sharded solve (comm.cu); world <= 1 means single GPU
-  void *nccl = nullptr;      // ncclComm_t
+struct CommState {           // communicator of a column-sharded solve (comm.cu); world <= 1 means single GPU
+  void *nccl = nullptr;      // ncclComm_t (large messages: the m x m Gram)
   int rank = 0, world = 0;
+  // peer-memory all-reduce for the small latency-bound messages (m-vectors, packed scalars): every rank exports one
+  // buffer over CUDA IPC; kernels store/load through the NVLink-mapped peer pointers
+  double *peer_local = nullptr;          // this rank's region (cudaMalloc)
+  double *peer_map[8] = {nullptr};       // peer_map[r] = rank r's region mapped into this process (peer_map[rank] = peer_local)
+  bool peer_ready = false;
+  unsigned long long epoch = 0;
 };
 
 struct lfpsqp_ctx {

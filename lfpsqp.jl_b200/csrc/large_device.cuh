@@ -1,0 +1,63 @@
+// large_device.cuh -- device helper functions shared by the large-n kernels and the communicator kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "large_ctrl.h"
+
+namespace lfpsqp {
+
+// NaN-propagating max (Julia's norm(x, Inf) returns NaN if any entry is NaN; fmax would drop it and a diverged
+// retraction would look converged)
+__device__ __forceinline__ double nanmax(double a, double b) { return (b > a || isnan(b)) ? b : a; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { double w = __shfl_xor_sync(0xffffffffu, v, o); v = (w > v || isnan(w)) ? w : v; }
+  return v;
+}
+// sum over the CTA (blockDim.x multiple of 32, <= 1024); result valid in every thread
+__device__ __forceinline__ double block_sum(double v, double *sh /* >= 33 doubles */) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double r = (lane < nw) ? sh[lane] : 0.0;
+  r = warp_sum(r);
+  return r;
+}
+__device__ __forceinline__ double block_max(double v, double *sh) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double r = (lane < nw) ? sh[lane] : 0.0;
+  r = warp_max(r);
+  return r;
+}
+// fixed-order sum of np partials by the whole CTA
+__device__ __forceinline__ double reduce_partials(const double *part, int np, double *sh) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) s += part[i];
+  return block_sum(s, sh);
+}
+__device__ __forceinline__ double reduce_partials_max(const double *part, int np, double *sh) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) { double w = part[i]; s = (w > s || isnan(w)) ? w : s; }
+  return block_max(s, sh);
+}
+
+__device__ __forceinline__ double2 ld_stream2(const double *p) {  // streaming 128-bit load, do not keep in L1
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+}  // namespace lfpsqp

@@ -51,7 +51,7 @@ def exchange_unique_id(make_id, dist, rank):
     return box[0]
 
 
-def init_comm(ctx, dist=None):
+def init_comm(ctx, dist=None, peer=True):
     """Create the library's NCCL communicator for this process group. Returns (rank, world)."""
     if dist is None:
         import torch.distributed as dist
@@ -68,6 +68,20 @@ def init_comm(ctx, dist=None):
 
     uid = exchange_unique_id(make_id, dist, rank)
     ctx.check(ctx.lib.lfpsqp_comm_init(ctx.h, rank, world, C.create_string_buffer(uid, 128), cpath))
+    if peer and 2 <= world <= 8:
+        # peer-memory all-reduce for the small messages: exchange CUDA IPC handles (rank order), map, barrier
+        hb = C.create_string_buffer(64)
+        ok = ctx.lib.lfpsqp_comm_ipc_export(ctx.h, hb) == 0
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(hb.raw) if ok else None)
+        if all(h is not None for h in handles):
+            rc = ctx.lib.lfpsqp_comm_ipc_import(ctx.h, C.create_string_buffer(b"".join(handles), 64 * world))
+            oks = [None] * world
+            dist.all_gather_object(oks, rc == 0)
+            if not all(oks):      # all or nothing: a mixed mode would deadlock the flag protocol
+                ctx.lib.lfpsqp_comm_destroy(ctx.h)
+                ctx.check(ctx.lib.lfpsqp_comm_init(ctx.h, rank, world, C.create_string_buffer(uid2 := exchange_unique_id(make_id, dist, rank), 128), cpath))
+        dist.barrier()
     return rank, world
 
 

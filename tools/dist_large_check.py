@@ -12,7 +12,8 @@ rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 ctx = L.Context(lr)
-D.init_comm(ctx, dist)
+D.init_comm(ctx, dist, peer=("nopeer" not in sys.argv))
+if rank == 0: print("comm mode", ctx.lib.lfpsqp_comm_mode(ctx.h), flush=True)
 dev = torch.device("cuda", lr)
 
 def rel(a, b): return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
