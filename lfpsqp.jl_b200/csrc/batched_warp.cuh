@@ -75,15 +75,21 @@ struct Solver {
   }
 
   // ------------------------------------------------------------ small vector helpers (all end with a group sync)
+  // the reductions end with a group barrier: a later write to the operands by another lane is then ordered after
+  // every lane's reads by the memory model (racecheck-clean), not merely by the shuffle's convergence
   LFPSQP_DEV double dot(const double *a, const double *b, int len) const {
     double s = 0;
     for (int i = g.lane; i < len; i += G::SIZE) s += a[i] * b[i];
-    return g.sum(s);
+    s = g.sum(s);
+    g.sync();
+    return s;
   }
   LFPSQP_DEV double norminf(const double *a, int len) const {
     double s = 0;
     for (int i = g.lane; i < len; i += G::SIZE) s = pmax(fabs(a[i]), s);
-    return g.maxabs(s);
+    s = g.maxabs(s);
+    g.sync();
+    return s;
   }
   LFPSQP_DEV void copy(double *dst, const double *src, int len) const {
     for (int i = g.lane; i < len; i += G::SIZE) dst[i] = src[i];
