@@ -32,6 +32,7 @@ extern "C" {
 #define LFPSQP_ERR_CUDA (-5)
 #define LFPSQP_ERR_NOMEM (-6)
 #define LFPSQP_ERR_COMM (-7)
+#define LFPSQP_ERR_CALLBACK (-8)   /* a host callback returned non-zero (the Julia wrapper rethrows the stored exception) */
 
 /* LFPSQPParams, src/LFPSQP.jl:57-81 (same defaults: lfpsqp_default_params). disp/callback are host-side
  * cosmetics of the reference and are ignored by the device path. */
@@ -82,8 +83,32 @@ enum {
                                 params = [Q (m x n row-major), A (m x n row-major), b(m), xt(n), w(n)] */
   LFPSQP_FAM_SIN = 5,        /* test/test_retractions.jl:34-54: c_i = x[2i]-sin(x[2i-1]); f=1/2|x-t|^2; params=t[n] */
   LFPSQP_FAM_BOXQUAD = 6,    /* f=|x-t|^2, optional c=a.x-b (m in {0,1}); params=[t(n), a(n), b] */
-  LFPSQP_FAM_COUNT = 7
+  LFPSQP_FAM_COUNT = 7,
+  LFPSQP_FAM_HOST = 100      /* generic problem: f / grad! / c! / jac! / hess_lag_vec! are HOST callbacks (lfpsqp_host_callbacks);
+                                large-n mode, one GPU.  The linear algebra runs on the device, the callbacks on the host. */
 };
+
+/*
+ * Host callbacks of the explicit-derivative core optimize(f, grad!, c!, jac!, hess_lag_vec!, x0, xl, xu, m, param)
+ * (src/optimize.jl:119-143).  Conventions are the reference's (src/autodiff_generators.jl:7-9, :40-42, :80-104):
+ * x is the first n entries of the working vector (optimize.jl:259 passes view(x, 1:n)); jac! fills Jc (m x n,
+ * COLUMN-major: Jc[i + j*m], optimize.jl:189) AND cval; hess_lag_vec! writes dest = (Hess f + sum_i lam_i Hess c_i) src.
+ * Every callback returns 0 on success; non-zero aborts the solve with LFPSQP_ERR_CALLBACK.  All pointers are host
+ * memory owned by the library (pinned), valid only during the call.  c and jac may be NULL iff m == 0.
+ * callback (optional) is param.callback(i, x) (optimize.jl:432-434; x has length n, or 2n with finite bounds), called when
+ * i % param.callback_period == 0.  randn (optional) must fill buf with standard normals (randn!(tmp_n), optimize.jl:264-273):
+ * it is what makes beta > 0 reproducible from the caller's own RNG stream; beta > 0 without it is LFPSQP_ERR_UNSUPPORTED.
+ */
+typedef struct {
+  void *user;
+  int (*f)(void *user, const double *x, int64_t n, double *fval);
+  int (*grad)(void *user, double *g, const double *x, int64_t n);
+  int (*c)(void *user, double *cval, const double *x, int64_t n, int64_t m);
+  int (*jac)(void *user, double *Jc, double *cval, const double *x, int64_t n, int64_t m);
+  int (*hess_lag_vec)(void *user, double *dest, const double *src, const double *x, const double *lam, int64_t n, int64_t m);
+  int (*callback)(void *user, int64_t iter, const double *x_aug, int64_t n_aug);
+  int (*randn)(void *user, double *buf, int64_t n_aug);
+} lfpsqp_host_callbacks;
 
 typedef struct lfpsqp_ctx lfpsqp_ctx;
 
@@ -126,7 +151,7 @@ int lfpsqp_solve_batched_dev(lfpsqp_ctx *ctx, int family, int64_t n, int64_t m, 
  * entries of every n-vector; m-vectors and the m x m factor are replicated; only the Gram, the m-vector J v and the
  * CG scalars are all-reduced.  Without a communicator col0 = 0, n_loc = n.
  */
-/* optimize(f, c!, x0, xl, xu, m, param) for one large instance on one GPU (fam_params, x0: host; xl/xu NULL or +-Inf) */
+/* optimize(f, c!, x0, xl, xu, m, param) for one large instance on one GPU (fam_params, x0, xl, xu: host; xl/xu may be NULL) */
 int lfpsqp_solve_large(lfpsqp_ctx *ctx, int family, int64_t n, int64_t m, const double *fam_params, const double *x0,
                        const double *xl, const double *xu, const lfpsqp_params *params, double *x_out, double *obj_hist,
                        int64_t H, int64_t *obj_len, double *lambda, lfpsqp_term *term, lfpsqp_stats *stats);
@@ -134,9 +159,18 @@ int lfpsqp_solve_large(lfpsqp_ctx *ctx, int family, int64_t n, int64_t m, const 
  * [Q_loc (m x n_loc row-major), A_loc (m x n_loc), b (m), xt_loc (n_loc), w_loc (n_loc)], host or device memory. */
 int lfpsqp_large_setup(lfpsqp_ctx *ctx, int family, int64_t n_global, int64_t m, int64_t col0, int64_t n_loc,
                        const double *params, int params_on_device);
+/* bounds of this rank's entries (both NULL, or all -Inf/+Inf on EVERY rank = no bounds: optimize.jl:151); errors as
+ * optimize.jl:144-148, :160-162.  Call on every rank (the "any finite bound" decision is all-reduced). */
+int lfpsqp_large_set_bounds(lfpsqp_ctx *ctx, const double *xl_loc, const double *xu_loc);
 int lfpsqp_large_solve(lfpsqp_ctx *ctx, const double *x0_loc, const lfpsqp_params *params, double *x_out_loc,
                        double *obj_hist, int64_t H, int64_t *obj_len, double *lambda, lfpsqp_term *term,
                        lfpsqp_stats *stats);
+/* the explicit-derivative core optimize(f, grad!, c!, jac!, hess_lag_vec!, x0, xl, xu, m, param) (src/optimize.jl:119-443)
+ * for an ARBITRARY problem given by host callbacks: = lfpsqp_large_setup(LFPSQP_FAM_HOST) + set_bounds + large_solve.
+ * lambda has length m.  The slack wrapper for d! (optimize.jl:13-71) stays on the host side, as in the reference. */
+int lfpsqp_solve_host(lfpsqp_ctx *ctx, const lfpsqp_host_callbacks *cb, int64_t n, int64_t m, const double *x0,
+                      const double *xl, const double *xu, const lfpsqp_params *params, double *x_out, double *obj_hist,
+                      int64_t H, int64_t *obj_len, double *lambda, lfpsqp_term *term, lfpsqp_stats *stats);
 /* unit-level ops mirroring the reference functions one to one (host buffers; outputs may be NULL):
  *   factor  : J = jac(x); G = J J' (m x m row-major, lower triangle valid), L = chol(G), Linv = L^-1   [ksvd!]
  *   project : v - J'(J J')^-1 J v and lambda = (J J')^-1 J v with the cached factor                    [kgemv! x2, optimize.jl:306-307, :333-343]

@@ -166,6 +166,11 @@ def optimize(*args, ctx=None, history=20000, return_stats=False):
     -> (x, obj_values, λ_kkt, term_info), as src/optimize.jl:442."""
     a = list(args)
     param = a.pop() if a and isinstance(a[-1], LFPSQPParams) else None
+    if len(a) == 9 and callable(a[0]) and not isinstance(a[0], DeviceCallback):
+        # the explicit-derivative core optimize(f, grad!, c!, jac!, hess_lag_vec!, x0, xl, xu, m, param) (optimize.jl:119)
+        # with host callables: generic problems, linear algebra on the device (host.py)
+        from .host import optimize_explicit
+        return optimize_explicit(*a, param, ctx=ctx, history=history, return_stats=return_stats)
     # locate x0 in the positional list and add the batch axis
     idx = {2: 1, 4: 2, 6: 2, 8: 3, 10: 5}.get(len(a))
     if idx is None:

@@ -4,7 +4,9 @@
 // O(mn) / O(m^2 n) operation is a hand-written kernel (large_gemm.cuh, large_kernels.cuh, large_families.cuh).
 // Inner loops (projcg!, pcg!) are device-predicated: their kernels test ctrl->status, so iterations are enqueued
 // in chunks and the host reads the control block once per chunk.
-// Bounds (the 2n-variable embedding) are not supported in this mode yet: BASELINE configs C4/C5 have none.
+// Finite bounds run the reference's 2n-variable embedding (src/inequality_helper.jl): working vectors become
+// [x-half | y-half] and the operators take the closed forms of large_ineq.cuh.  LFPSQP_FAM_HOST evaluates f / grad! /
+// c! / jac! / hess_lag_vec! through host callbacks (the explicit-derivative core, optimize.jl:119): generic problems.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -17,6 +19,7 @@
 #include "large_gemm.cuh"
 #include "large_kernels.cuh"
 #include "large_families.cuh"
+#include "large_ineq.cuh"
 #include "large_state.h"
 
 using namespace lfpsqp;
@@ -117,8 +120,22 @@ static void thomson_grid(LargeState &S, int np, dim3 &grid) {
   int js = std::max(1, std::min(16, (2 * S.sm_count) / ib));
   grid = dim3(ib, js);
 }
+// ---- host-callback family: the first n entries of a device vector -> pinned S.hx (blocking; also orders every earlier
+// H2D copy out of the pinned staging buffers before the callback may overwrite them)
+static void host_x(LargeState &S, const double *x) {
+  cudaMemcpyAsync(S.hx, x, S.n_loc * sizeof(double), cudaMemcpyDeviceToHost, S.stream);
+  cudaStreamSynchronize(S.stream);
+}
+__global__ void set_partials_kernel(double *part, int np, double v) {
+  for (int i = threadIdx.x; i < np; i += blockDim.x) part[i] = (i == 0) ? v : 0.0;
+}
 static void fam_f(LargeState &S, const double *x) {  // -> gpart slot 0 (sum); caller finalizes s[0]
-  if (S.family == LFPSQP_FAM_DIAGQUAD) {
+  if (S.family == LFPSQP_FAM_HOST) {
+    host_x(S, x);
+    double fv = NAN;
+    if (S.cb.f(S.cb.user, S.hx, S.n, &fv)) S.cb_err = 1;
+    set_partials_kernel<<<1, 256, 0, S.stream>>>(S.gpart, S.vgrid, fv);
+  } else if (S.family == LFPSQP_FAM_DIAGQUAD) {
     const double *xt = S.p_xt, *w = S.p_w;
     vec(S, S.n_loc, [=] __device__(int64_t j, double *acc) { double t = x[j] - xt[j]; acc[0] += 0.5 * w[j] * t * t; }, 0, 1);
   } else {
@@ -131,7 +148,11 @@ static void fam_f(LargeState &S, const double *x) {  // -> gpart slot 0 (sum); c
   S.launches++; S.f_evals++;
 }
 static void fam_grad(LargeState &S, double *g, const double *x) {
-  if (S.family == LFPSQP_FAM_DIAGQUAD) {
+  if (S.family == LFPSQP_FAM_HOST) {
+    host_x(S, x);
+    if (S.cb.grad(S.cb.user, S.hv, S.hx, S.n)) S.cb_err = 1;
+    cudaMemcpyAsync(g, S.hv, S.n_loc * sizeof(double), cudaMemcpyHostToDevice, S.stream);
+  } else if (S.family == LFPSQP_FAM_DIAGQUAD) {
     const double *xt = S.p_xt, *w = S.p_w;
     vec(S, S.n_loc, [=] __device__(int64_t j, double *) { g[j] = w[j] * (x[j] - xt[j]); });
   } else {
@@ -146,7 +167,17 @@ static void fam_grad(LargeState &S, double *g, const double *x) {
 // cval = c(x); with Jout also the Jacobian (jac! writes both, autodiff_generators.jl:40-42)
 static void fam_c_jac(LargeState &S, double *Jout, double *cval, const double *x) {
   const int m = S.m;
-  if (S.family == LFPSQP_FAM_DIAGQUAD) {
+  if (S.family == LFPSQP_FAM_HOST) {
+    host_x(S, x);
+    if (Jout) {  // jac!(Jc, cval, x): Jc is m x n column-major (optimize.jl:189) = n x m row-major -> transposed into J (= Jct)
+      if (S.cb.jac(S.cb.user, S.hJ, S.hc, S.hx, S.n, m)) S.cb_err = 1;
+      cudaMemcpyAsync(S.Jstage, S.hJ, (size_t)m * S.n_loc * sizeof(double), cudaMemcpyHostToDevice, S.stream);
+      dim3 tg((m + 31) / 32, (unsigned)((S.n_loc + 31) / 32));
+      transpose_kernel<<<tg, 256, 0, S.stream>>>(S.Jstage, m, Jout, S.ldj, (int)S.n_loc, m);
+    } else if (S.cb.c(S.cb.user, S.hc, S.hx, S.n, m)) S.cb_err = 1;
+    cudaMemcpyAsync(cval, S.hc, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, S.stream);
+    S.launches++;
+  } else if (S.family == LFPSQP_FAM_DIAGQUAD) {
     if (Jout) dq_rows_kernel<2, true><<<(m + 1) / 2, 256, 0, S.stream>>>(S.p_Q, S.p_A, S.ldj, m, S.n_loc, x, Jout, cval);
     else dq_rows_kernel<2, false><<<(m + 1) / 2, 256, 0, S.stream>>>(S.p_Q, S.p_A, S.ldj, m, S.n_loc, x, nullptr, cval);
     if (S.world > 1) comm_allreduce(S, cval, m);
@@ -161,13 +192,18 @@ static void fam_c_jac(LargeState &S, double *Jout, double *cval, const double *x
 }
 // per outer iteration: whatever of the Lagrangian Hessian depends only on (x, lambda)
 static void fam_hess_prepare(LargeState &S, const double *x, const double *lam) {
-  (void)x;
-  if (S.family == LFPSQP_FAM_DIAGQUAD) {  // hdiag = w + Q' lambda : one pass over Q
+  if (S.family == LFPSQP_FAM_HOST) {  // the closure of optimize.jl:227-231 reads the current x and lambda: cache them on the host
+    host_x(S, x);
+    if (S.m > 0) { cudaMemcpyAsync(S.hlam, lam, S.m * sizeof(double), cudaMemcpyDeviceToHost, S.stream); cudaStreamSynchronize(S.stream); }
+  } else if (S.family == LFPSQP_FAM_DIAGQUAD) {  // hdiag = w + Q' lambda : one pass over Q
     cols_dot(S, S.p_Q, S.ldj, S.m, S.n_loc, lam, 0);
-    const double *cp = S.cpart, *w = S.p_w; double *hd = S.hdiag; int ns = S.nsplit; int64_t n = S.n_loc;
+    const double *cp = S.cpart, *w = S.p_w; double *hd = S.hdiag; int ns = S.m > 0 ? S.nsplit : 0; int64_t n = S.n_loc;
+    const lfpsqp::IneqDev I = S.I; const bool ineq = S.ineq;
+    // with bounds the augmented terms of inequality_helper.jl:144-158 are diagonal too: fold them into hdiag (2n entries)
     vec(S, n, [=] __device__(int64_t j, double *) {
       double s = w[j];
       for (int k = 0; k < ns; k++) s += cp[(int64_t)k * n + j];
+      if (ineq) { const double ly2 = 2.0 * I.lamy[j]; s += ly2 * I.q[j]; hd[n + j] = ly2 * I.s[j]; }
       hd[j] = s;
     });
     S.launches++;
@@ -175,10 +211,18 @@ static void fam_hess_prepare(LargeState &S, const double *x, const double *lam) 
 }
 // dest = H src, partial src.dest -> loop-partial slot 0 ; returns the number of partials written
 static int fam_hess(LargeState &S, double *dest, const double *src, const double *x, const double *lam, int pred) {
-  if (S.family == LFPSQP_FAM_DIAGQUAD) {
+  if (S.family == LFPSQP_FAM_HOST) {  // the caller has checked ctrl->status on the host (chunk = 1)
+    cudaMemcpyAsync(S.hw, src, S.n_loc * sizeof(double), cudaMemcpyDeviceToHost, S.stream);
+    cudaStreamSynchronize(S.stream);
+    if (S.cb.hess_lag_vec(S.cb.user, S.hv, S.hw, S.hx, S.hlam, S.n, S.m)) S.cb_err = 1;
+    cudaMemcpyAsync(dest, S.hv, S.n_loc * sizeof(double), cudaMemcpyHostToDevice, S.stream);
+    if (!S.ineq) dot_partials_kernel<<<S.vgrid, 256, 0, S.stream>>>(S.n_loc, src, dest, S.lp, 0, S.ctrl, pred);
+    S.launches++;
+    return S.vgrid;
+  } else if (S.family == LFPSQP_FAM_DIAGQUAD) {
     const double *hd = S.hdiag; const LargeCtrl *ctrl = S.ctrl; double *lp = S.lp;
-    // predicated elementwise kernel with the d.Ad partial
-    hess_diag_kernel<<<S.vgrid, 256, 0, S.stream>>>(S.n_loc, hd, src, dest, lp, ctrl, pred);
+    // predicated elementwise kernel with the d.Ad partial (hdiag carries the bound terms: nv entries)
+    hess_diag_kernel<<<S.vgrid, 256, 0, S.stream>>>(S.nv, hd, src, dest, lp, ctrl, pred);
     S.launches++;
     return S.vgrid;
   } else {
@@ -191,11 +235,51 @@ static int fam_hess(LargeState &S, double *dest, const double *src, const double
   }
 }
 
+// Lagrangian Hessian action on the working vector: the family's on the x-half plus, with bounds, the augmented terms
+// (augmented_hess_lag_vec!, inequality_helper.jl:144-158); src.dest partials -> loop slot 0
+static int hess_apply(LargeState &S, double *dest, const double *src, int pred) {
+  int nph = fam_hess(S, dest, src, S.x, S.lam, pred);
+  if (S.ineq && S.family != LFPSQP_FAM_DIAGQUAD) {
+    ineq_hess_aug_kernel<<<S.vgrid, 256, 0, S.stream>>>(S.I, dest, src, S.lp, S.ctrl, pred);
+    S.launches++;
+    nph = S.vgrid;
+  }
+  return nph;
+}
+
+// ------------------------------------------------------------------ bound embedding: one-off elementwise operations
+static void ineq_gradient(LargeState &S, const double *v) {  // inequality_gradient! (inequality_helper.jl:125-141)
+  const lfpsqp::IneqDev I = S.I;
+  vec(S, I.nx, [=] __device__(int64_t j, double *) {
+    double Dx, Dy, Sv;
+    ineq_grad(I.q[j], I.r[j], I.s[j], v[j], v[I.nx + j], Dx, Dy, Sv);
+    I.Dx[j] = Dx; I.Dy[j] = Dy; I.S[j] = Sv;
+  });
+  S.launches++;
+}
+static void y_retract(LargeState &S, double *vn, const double *vb) {  // y_retract! (retractions.jl:451-500)
+  const lfpsqp::IneqDev I = S.I;
+  vec(S, I.nx, [=] __device__(int64_t j, double *) {
+    double xn = vn[j], yn = vn[I.nx + j];
+    ineq_yretract(I.q[j], I.r[j], I.s[j], I.t[j], vb[j], vb[I.nx + j], xn, yn);
+    vn[j] = xn; vn[I.nx + j] = yn;
+  });
+  S.launches++;
+}
+
 // ------------------------------------------------------------------ factorisation: G = J J' = L L', XT = L^-T, Linv = L^-1
+// (with bounds G = J diag(Dy^2) J' = PJct' PJct, optimize.jl:288-289 / SURVEY App. B)
 static int factorize(lfpsqp_ctx *c, LargeState &S) {
   const int m = S.m; const int64_t ldm = S.ldm;
+  const double *Jg = S.J;
+  if (S.ineq) {
+    dim3 sg((unsigned)std::min<int64_t>(std::max<int64_t>(((S.n_loc >> 1) + 255) / 256, 1), 32), (unsigned)std::min(m, 65535));
+    ineq_scale_cols_kernel<<<sg, 256, 0, S.stream>>>(S.J, S.ldj, m, S.n_loc, S.I.Dy, S.Jw);
+    S.launches++;
+    Jg = S.Jw;
+  }
   cudaEventRecord(S.ev_g0, S.stream);
-  gemm_nt(S, m, m, (int)S.n_loc, S.J, S.ldj, S.J, S.ldj, S.G, ldm, GEMM_ASSIGN, 1);   // SYRK, lower tiles
+  gemm_nt(S, m, m, (int)S.n_loc, Jg, S.ldj, Jg, S.ldj, S.G, ldm, GEMM_ASSIGN, 1);   // SYRK, lower tiles
   cudaEventRecord(S.ev_g1, S.stream);
   if (S.world > 1) comm_allreduce(S, S.G, (size_t)m * ldm);
   diag_thresh_kernel<<<1, 256, 0, S.stream>>>(S.G, ldm, m, S.prm.eps_rank, S.thresh);
@@ -235,37 +319,61 @@ static int factorize(lfpsqp_ctx *c, LargeState &S) {
 
 // v <- v - J'(J J')^-1 J v ; with lam_out the multipliers u = (J J')^-1 J v  (optimize.jl:306-307, :333-343 ; App. B)
 // partial sums of the projected vector: slot0 = sum v^2, slot3 = max |v| (when want_norms)
-static void project(LargeState &S, double *v, double *lam_out, int pred, int want_norms) {
-  rows_dot(S, S.J, S.ldj, S.m, S.n_loc, v, S.tm, pred);
+// the passes over J of one projection: cpart = J' G^-1 J o with o = v, or with bounds o = Dy (Dy v_x - Dx v_y) (PJct' v);
+// lam_out = G^-1 J o.  The elementwise tail (v - ...) is fused into the caller's next kernel.
+static void proj_passes(LargeState &S, const double *v, double *lam_out, int pred) {
+  const double *operand = v;
+  if (S.ineq) {
+    ineq_proj_pre_kernel<<<S.vgrid, 256, 0, S.stream>>>(S.I, v, S.pb, S.ctrl, pred);
+    S.launches++;
+    operand = S.pb;
+  }
+  if (S.m <= 0) return;
+  rows_dot(S, S.J, S.ldj, S.m, S.n_loc, operand, S.tm, pred);
   if (S.world > 1) comm_allreduce(S, S.tm, S.m);
   gram_solve(S, S.tm, S.tu, lam_out, pred);
   cols_dot(S, S.J, S.ldj, S.m, S.n_loc, S.tu, pred);
-  const double *cp = S.cpart; int ns = S.nsplit; int64_t n = S.n_loc;
-  vec(S, n, [=] __device__(int64_t j, double *acc) {
-    double s = 0.0;
-    for (int k = 0; k < ns; k++) s += cp[(int64_t)k * n + j];
-    double r = v[j] - s; v[j] = r;
-    acc[0] += r * r; acc[3] = nanmax(acc[3], fabs(r));
-  }, 0, want_norms ? 1 : 0, want_norms);
+}
+static void project(LargeState &S, double *v, double *lam_out, int pred, int want_norms, int want_mult = 0) {
+  proj_passes(S, v, lam_out, pred);
+  const double *cp = S.cpart; int ns = S.m > 0 ? S.nsplit : 0; int64_t n = S.n_loc;
+  if (!S.ineq) {
+    vec(S, n, [=] __device__(int64_t j, double *acc) {
+      double s = 0.0;
+      for (int k = 0; k < ns; k++) s += cp[(int64_t)k * n + j];
+      double r = v[j] - s; v[j] = r;
+      acc[0] += r * r; acc[3] = nanmax(acc[3], fabs(r));
+    }, 0, want_norms ? 1 : 0, want_norms);
+  } else {  // d - Q Q'd (optimize.jl:314-317) and lambda_y (calculate_lambda_kkt!, inequality_helper.jl:286-308)
+    const lfpsqp::IneqDev I = S.I;
+    vec(S, n, [=] __device__(int64_t j, double *acc) {
+      double ox, oy, aa, wj;
+      ineq_proj_tail(I, j, v[j], v[I.nx + j], cp, ns, ox, oy, aa, wj);
+      v[j] = ox; v[I.nx + j] = oy;
+      if (want_mult) I.lamy[j] = -1.0 * (I.Dx[j] / I.S[j]) * wj + aa / I.S[j];
+      acc[0] += ox * ox + oy * oy; acc[3] = nanmax(acc[3], nanmax(fabs(ox), fabs(oy)));
+    }, 0, want_norms ? 1 : 0, want_norms);
+  }
   S.launches++;
 }
 
 // ------------------------------------------------------------------ projcg! (projcg.jl:40-121), c = 0
 // b = S.d (projected -grad). Solution -> S.nd. Fills S.hctrl (status/iter/nr) on return.
 static int projcg(lfpsqp_ctx *c, LargeState &S, double tol, int64_t maxit, int chunk) {
-  const int64_t n = S.n_loc;
+  const int64_t n = S.nv;   // working length: n_loc, or 2 n_loc with bounds
+  const int ns = S.m > 0 ? S.nsplit : 0;
   double *xs = S.nd, *r = S.w0, *dc = S.w1, *Ad = S.w2, *rp = S.w3, *gp = S.w4;
   const double *b = S.d;
+  if (S.family == LFPSQP_FAM_HOST) chunk = 1;   // the Hessian callback runs on the host: one status check per iteration
   vec(S, n, [=] __device__(int64_t i, double *) { xs[i] = 0.0; r[i] = -b[i]; });
   // g = r - U U' r (projcg.jl:59-60) ; r = g ; d = -g ; rg partials -> loop slot 3 (= 2 + (par^1) for k = 0)
-  rows_dot(S, S.J, S.ldj, S.m, n, r, S.tm, 0);
-  if (S.world > 1) comm_allreduce(S, S.tm, S.m);
-  gram_solve(S, S.tm, S.tu, nullptr, 0);
-  cols_dot(S, S.J, S.ldj, S.m, n, S.tu, 0);
-  cg_init_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, r, dc, S.cpart, S.nsplit, S.lp);
+  proj_passes(S, r, nullptr, 0);
+  if (S.ineq) ineq_cg_init_kernel<<<S.vgrid, 256, 0, S.stream>>>(S.I, r, dc, S.cpart, ns, S.lp);
+  else cg_init_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, r, dc, S.cpart, ns, S.lp);
   if (S.world > 1) comm_allreduce_loop_slot(S, 3, S.np_loop_raw);
   S.launches += 2;
-  int64_t lim = std::min<int64_t>(maxit, S.n + S.m);   // min(maxit, n+m) with m = length(c) = rank (projcg.jl:71)
+  // min(maxit, n + length(c)) (projcg.jl:71): c has length rank = m, or n + rank with the bound projector (optimize.jl:366-372)
+  int64_t lim = std::min<int64_t>(maxit, S.ineq ? 3 * S.n + S.m : S.n + S.m);
   S.hctrl->tol = tol; S.hctrl->lim = (int)std::min<int64_t>(lim, 2000000000); S.hctrl->iter = 0; S.hctrl->status = (lim > 0) ? 0 : 4;
   S.hctrl->nr = INFINITY;
   write_ctrl_fields(S);
@@ -273,19 +381,17 @@ static int projcg(lfpsqp_ctx *c, LargeState &S, double tol, int64_t maxit, int c
   while (S.hctrl->status == 0) {
     for (int q = 0; q < chunk; q++, k++) {
       const int par = (int)(k & 1);
-      int nph = fam_hess(S, Ad, dc, S.x, S.lam, 1);
+      int nph = hess_apply(S, Ad, dc, 1);
       if (S.world > 1) comm_allreduce_loop_slot(S, 0, nph), nph = 1;
       cg_update1_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, xs, dc, r, Ad, rp, S.lp, nph, S.np_loop, par, S.ctrl);
-      rows_dot(S, S.J, S.ldj, S.m, n, rp, S.tm, 1);
-      if (S.world > 1) comm_allreduce(S, S.tm, S.m);
-      gram_solve(S, S.tm, S.tu, nullptr, 1);
-      cols_dot(S, S.J, S.ldj, S.m, n, S.tu, 1);
-      cg_update2_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, rp, gp, S.cpart, S.nsplit, S.lp, par, S.ctrl, 1);
+      proj_passes(S, rp, nullptr, 1);
+      if (S.ineq) ineq_cg_update2_kernel<<<S.vgrid, 256, 0, S.stream>>>(S.I, rp, gp, S.cpart, ns, S.lp, par, S.ctrl, 1);
+      else cg_update2_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, rp, gp, S.cpart, ns, S.lp, par, S.ctrl, 1);
       if (S.world > 1) comm_allreduce_loop_slots_cg(S, par);
       cg_update3_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, dc, r, gp, S.lp, S.np_loop, par, S.ctrl);
       S.launches += 3;
     }
-    if (read_ctrl(c, S)) return -1;
+    if (read_ctrl(c, S) || S.cb_err) return -1;
   }
   S.projcg_iters += S.hctrl->iter;
   if (S.hctrl->status == 2) {  // negative curvature: x = d/|d| (projcg.jl:77-82)
@@ -304,7 +410,7 @@ static int projcg(lfpsqp_ctx *c, LargeState &S, double tol, int64_t maxit, int c
 // state: dx = S.w3 (initial guess), r = S.w0 (= b - A dx), p = S.w1 (zeroed by the caller), z = S.w2;
 // r.r partials of the start residual in loop slot 5.  Device-predicated, enqueued in chunks.
 static int run_pcg(lfpsqp_ctx *c, LargeState &S, double mu, double tol, int64_t maxiter) {
-  const int64_t n = S.n_loc; const int m = S.m;
+  const int64_t n = S.nv, nx = S.n_loc; const int m = S.m;
   double *r = S.w0, *pv = S.w1, *z = S.w2, *dx = S.w3;
   S.hctrl->tol = tol; S.hctrl->mu = mu; S.hctrl->pcg_iter = 0; S.hctrl->pcg_lim = (int)std::min<int64_t>(maxiter, 2000000000); S.hctrl->pcg_status = 0;
   write_ctrl_fields(S);
@@ -314,10 +420,11 @@ static int run_pcg(lfpsqp_ctx *c, LargeState &S, double mu, double tol, int64_t 
       const int par = (int)(k & 1);
       if (S.world > 1) comm_allreduce_loop_slot(S, 5 + par, S.np_loop_raw);
       pcg_a_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, pv, r, S.lp, S.np_loop, par, k == 0, S.ctrl);
-      rows_dot(S, S.J, S.ldj, m, n, pv, S.tm, 2);
+      rows_dot(S, S.J, S.ldj, m, nx, pv, S.tm, 2);     // J p_x (bigA' p = [S (Dx p_x + Dy p_y) ; J p_x] with bounds)
       if (S.world > 1) comm_allreduce(S, S.tm, m);
-      cols_dot(S, S.J, S.ldj, m, n, S.tm, 2);
-      pcg_z_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, z, pv, S.cpart, S.nsplit, S.lp, S.ctrl);
+      cols_dot(S, S.J, S.ldj, m, nx, S.tm, 2);
+      if (S.ineq) ineq_pcg_z_kernel<<<S.vgrid, 256, 0, S.stream>>>(S.I, z, pv, S.cpart, S.nsplit, S.lp, S.ctrl);
+      else pcg_z_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, z, pv, S.cpart, S.nsplit, S.lp, S.ctrl);
       if (S.world > 1) comm_allreduce_loop_slot(S, 4, S.np_loop_raw);
       pcg_x_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, dx, r, pv, z, S.lp, S.np_loop, par, S.ctrl);
       S.launches += 3;
@@ -330,69 +437,105 @@ static int run_pcg(lfpsqp_ctx *c, LargeState &S, double mu, double tol, int64_t 
 // ------------------------------------------------------------------ retract!(::ProjPenalty) (retractions.jl:265-441) + pcg! (:179-246)
 // xtil -> xnew ; returns flag, it1 (outer), it2 (pcg total)
 static int retract_pp(lfpsqp_ctx *c, LargeState &S, int *flag_out, int *it1, int *it2) {
-  const int64_t n = S.n_loc; const int m = S.m;
-  double *r = S.w0, *pv = S.w1, *z = S.w2, *dx = S.w3, *gv = S.w4, *xnew = S.xnew, *cval = S.cval;
+  const int64_t n = S.n_loc, nv = S.nv; const int m = S.m;
+  const bool ineq = S.ineq; const lfpsqp::IneqDev I = S.I;
+  double *r = S.w0, *pv = S.w1, *z = S.w2, *dx = S.w3, *gv = S.w4, *xnew = S.xnew, *cval = S.cval, *cvh = S.cvh, *cvc = S.cvc;
   const double *xtil = S.xtil;
   const lfpsqp_params &prm = S.prm;
+  auto hmax = [](double a, double b) { return (b > a || std::isnan(b)) ? b : a; };
   int flag = 0;
-  cudaMemcpyAsync(xnew, xtil, n * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);
+  (void)z;
+  cudaMemcpyAsync(xnew, xtil, nv * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);
   double mu = prm.mu0;
   int i = 0, pcg_total = 0;
   while (i < prm.maxiter_retract) {
     fam_c_jac(S, S.J, cval, xnew);                                                       // :340
-    // curtol = |c|_inf (slot 3 max), c.c (slot 0) ; g = xnew - xtilde, g.g (slot 1)
-    vec(S, m, [=] __device__(int64_t a, double *acc) { double v = cval[a]; acc[0] += v * v; acc[3] = nanmax(acc[3], fabs(v)); }, 0, 1, 1);
-    finalize(S, 1u, 8u, 1u | 8u);
-    if (read_ctrl(c, S)) return -1;
-    double curtol = S.hctrl->s[3], cc = S.hctrl->s[0];
-    if (curtol < prm.eps_c) break;                                                       // :359-361
-    vec(S, n, [=] __device__(int64_t k, double *acc) { double t = xnew[k] - xtil[k]; gv[k] = t; acc[1] += t * t; }, 0, 2);
-    finalize(S, 2u, 0);
-    // g = J' c + mu g (:369) ; dx = 0 ; r = g ; r.r partials -> loop slot 5 (rho_0)
-    cols_dot(S, S.J, S.ldj, m, n, cval, 0);
-    {
-      const double *cp = S.cpart; int ns = S.nsplit; double *lp = S.lp; double muv = mu;
-      pp_rhs_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, gv, dx, r, pv, cp, ns, muv, lp);
+    // curtol = |c|_inf (slot 3 max), c.c (slot 0) ; with bounds also |h|_inf (slot 4), h.h (slot 1) and the stale tail
+    if (!ineq) {
+      vec(S, m, [=] __device__(int64_t a, double *acc) { double v = cval[a]; acc[0] += v * v; acc[3] = nanmax(acc[3], fabs(v)); }, 0, 1, 1);
+    } else {
+      // inequality_gradient! on the shared decomposition (:343-347) ; h -> cvalaug[1:n] (:350)
+      vec(S, n, [=] __device__(int64_t j, double *acc) {
+        const double xv = xnew[j], yv = xnew[n + j];
+        double Dx, Dy, Sv;
+        ineq_grad(I.q[j], I.r[j], I.s[j], xv, yv, Dx, Dy, Sv);
+        I.Dx[j] = Dx; I.Dy[j] = Dy; I.S[j] = Sv;
+        const double h = ineq_h(I.q[j], I.r[j], I.s[j], I.t[j], xv, yv);
+        cvh[j] = h; acc[0] += h * h; acc[3] = nanmax(acc[3], fabs(h));
+      }, 1, 1, 1);
+      // :352 takes the norm of ALL of cvalaug, whose tail still holds the previous c values; then :356 refreshes the tail
+      vec(S, m, [=] __device__(int64_t a, double *acc) {
+        const double v = cval[a];
+        acc[3] = nanmax(acc[3], nanmax(fabs(v), fabs(cvc[a])));
+        cvc[a] = v; acc[0] += v * v;
+      }, 0, 1, 1);
       S.launches++;
     }
-    if (read_ctrl(c, S)) return -1;
-    double prev_obj = cc + mu * S.hctrl->s[1];                                           // :366
+    // g = xnew - xtilde, g.g (slot 2)
+    vec(S, nv, [=] __device__(int64_t k, double *acc) { double t = xnew[k] - xtil[k]; gv[k] = t; acc[0] += t * t; }, 2, 1);
+    finalize(S, ineq ? (1u | 2u | 4u) : (1u | 4u), ineq ? (8u | 16u) : 8u, 1u | 8u);
+    S.launches += 2;
+    if (read_ctrl(c, S) || S.cb_err) return -1;
+    const double curtol = ineq ? hmax(S.hctrl->s[3], S.hctrl->s[4]) : S.hctrl->s[3];
+    const double cc = S.hctrl->s[0], hh = ineq ? S.hctrl->s[1] : 0.0, gg = S.hctrl->s[2];
+    if (curtol < prm.eps_c) break;                                                       // :359-361
+    const double prev_obj = (hh + cc) + mu * gg;                                         // :366
+    // g = J' c + mu g, or bigA [h ; c] + mu g (:369) ; dx = 0 ; r = g ; r.r partials -> loop slot 5 (rho_0)
+    cols_dot(S, S.J, S.ldj, m, n, cval, 0);
+    if (ineq) ineq_pp_rhs_kernel<<<S.vgrid, 256, 0, S.stream>>>(I, gv, dx, r, pv, S.cpart, S.nsplit, mu, cvh, S.lp);
+    else pp_rhs_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, gv, dx, r, pv, S.cpart, S.nsplit, mu, S.lp);
+    S.launches++;
     if (run_pcg(c, S, mu, prm.eps_c, prm.maxiter_pcg)) return -1;                       // :375
     int pcg_i = S.hctrl->pcg_iter;
     pcg_total += pcg_i;
     if (pcg_i == prm.maxiter_pcg) { flag = 2; break; }                                   // :240-243, :377-381
     // inner Armijo (:384-426)
-    vec(S, n, [=] __device__(int64_t q, double *acc) {
+    vec(S, nv, [=] __device__(int64_t q, double *acc) {
       double xk = xnew[q]; pv[q] = xk;
       acc[0] += gv[q] * dx[q];                     // ar_dot = -g.dx
       xk -= dx[q]; xnew[q] = xk;
       double t = xk - xtil[q]; gv[q] = t; acc[1] += t * t;
     }, 0, 2);
     fam_c_jac(S, nullptr, cval, xnew);                                                    // :392
-    vec(S, m, [=] __device__(int64_t a, double *acc) { double v = cval[a]; acc[0] += v * v; }, 2, 1);   // slot 2 only
+    vec(S, m, [=] __device__(int64_t a, double *acc) { double v = cval[a]; if (ineq) cvc[a] = v; acc[0] += v * v; }, 2, 1);   // slot 2 only
+    if (ineq) {                                                                           // h -> cvalaug[1:n] (:395-397), slot 4
+      vec(S, n, [=] __device__(int64_t j, double *acc) {
+        const double h = ineq_h(I.q[j], I.r[j], I.s[j], I.t[j], xnew[j], xnew[n + j]);
+        cvh[j] = h; acc[0] += h * h;
+      }, 4, 1);
+      S.launches++;
+    }
     S.launches += 2;
-    finalize(S, 7u, 0, 4u);
-    if (read_ctrl(c, S)) return -1;
-    double ar_dot = -S.hctrl->s[0], dist2 = S.hctrl->s[1], ccnew = S.hctrl->s[2];
+    finalize(S, ineq ? (7u | 16u) : 7u, 0, 4u);
+    if (read_ctrl(c, S) || S.cb_err) return -1;
+    double ar_dot = -S.hctrl->s[0], dist2 = S.hctrl->s[1], ccnew = S.hctrl->s[2], hhnew = ineq ? S.hctrl->s[4] : 0.0;
     double alpha = 1.0;
     int armijo_count = 0;
-    while (ccnew + mu * dist2 > prev_obj + 1e-4 * alpha * ar_dot) {                      // :403
+    while ((hhnew + ccnew) + mu * dist2 > prev_obj + 1e-4 * alpha * ar_dot) {            // :403
       alpha /= 2;
       double al = alpha;
-      vec(S, n, [=] __device__(int64_t q, double *acc) {
+      vec(S, nv, [=] __device__(int64_t q, double *acc) {
         double xk = pv[q] - al * dx[q]; xnew[q] = xk;
         double t = xk - xtil[q]; gv[q] = t; acc[0] += t * t;
       }, 1, 1);                                                                           // slot 1 only
       S.launches++;
-      finalize(S, 2u, 0);
+      if (ineq) {   // :413-415: the bound part of the merit IS refreshed during backtracking
+        vec(S, n, [=] __device__(int64_t j, double *acc) {
+          const double h = ineq_h(I.q[j], I.r[j], I.s[j], I.t[j], xnew[j], xnew[n + j]);
+          cvh[j] = h; acc[0] += h * h;
+        }, 4, 1);
+        S.launches++;
+      }
+      finalize(S, ineq ? (2u | 16u) : 2u, 0);
       if (read_ctrl(c, S)) return -1;
       dist2 = S.hctrl->s[1];
+      if (ineq) hhnew = S.hctrl->s[4];
       // :410-417: the c-part of the merit stays frozen at its alpha = 1 value (stale cval quirk)
       armijo_count++; S.pp_backtracks++;
       if (armijo_count == 100) { flag = 3; break; }
     }
     i++;
-    mu = std::min(mu * 0.1, sqrt(ccnew));                                                // :431 (norm of the stale cvalaug)
+    mu = std::min(mu * 0.1, sqrt(hhnew + ccnew));                                        // :431 (norm of the stale cvalaug)
   }
   if (i == prm.maxiter_retract) flag = 1;
   *flag_out = flag; *it1 = i; *it2 = pcg_total;
@@ -403,14 +546,16 @@ static int retract_pp(lfpsqp_ctx *c, LargeState &S, int *flag_out, int *it1, int
 static int retract_nr(lfpsqp_ctx *c, LargeState &S, int *flag_out, int *it1) {
   const int64_t n = S.n_loc; const int m = S.m; const int64_t ldm = S.ldm;
   double *xnew = S.xnew, *cval = S.cval, *D = S.Dnr, *t1 = S.nr_t1, *t2 = S.nr_t2, *dcv = S.nr_dc;
-  cudaMemcpyAsync(xnew, S.xtil, n * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);
+  const bool ineq = S.ineq; const lfpsqp::IneqDev I = S.I; const double *xb = S.x;
+  cudaMemcpyAsync(xnew, S.xtil, S.nv * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);
+  if (ineq) y_retract(S, xnew, xb);                                                      // :118-123
   fam_c_jac(S, nullptr, cval, xnew);
   cudaMemcpyAsync(D, S.Linv, (size_t)m * ldm * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);   // D0 = L^-1
   int i = 0;
   while (i < S.prm.maxiter_retract) {
     vec(S, m, [=] __device__(int64_t a, double *acc) { acc[3] = nanmax(acc[3], fabs(cval[a])); }, 0, 0, 1);
     finalize(S, 0, 8u, 8u);
-    if (read_ctrl(c, S)) return -1;
+    if (read_ctrl(c, S) || S.cb_err) return -1;
     if (S.hctrl->s[3] < S.prm.eps_c) break;                                              // :135
     rows_dot(S, D, ldm, m, m, cval, t1, 0);                                              // D c
     vec(S, m, [=] __device__(int64_t a, double *) { t1[a] = -t1[a]; });                   // :140 delta = -D c
@@ -418,7 +563,15 @@ static int retract_nr(lfpsqp_ctx *c, LargeState &S, int *flag_out, int *it1) {
     tri_gemv_kernel<<<(m + 7) / 8, 256, m * sizeof(double), S.stream>>>(S.XT, ldm, m, t1, S.tu, 1, nullptr, S.ctrl, 0);
     cols_dot(S, S.J, S.ldj, m, n, S.tu, 0);
     { const double *cp = S.cpart; int ns = S.nsplit;
-      vec(S, n, [=] __device__(int64_t j, double *) { double s = 0.0; for (int k = 0; k < ns; k++) s += cp[(int64_t)k * n + j]; xnew[j] += s; }); }
+      // with bounds the basis is Q = PJct L^-T: x += Dy^2 w, y -= Dx Dy w, then y_retract! (:141-143)
+      vec(S, n, [=] __device__(int64_t j, double *) {
+        double s = 0.0; for (int k = 0; k < ns; k++) s += cp[(int64_t)k * n + j];
+        if (!ineq) { xnew[j] += s; return; }
+        const double dx = I.Dx[j], dy = I.Dy[j];
+        double xn = xnew[j] + dy * dy * s, yn = xnew[n + j] - dx * dy * s;
+        ineq_yretract(I.q[j], I.r[j], I.s[j], I.t[j], xb[j], xb[n + j], xn, yn);
+        xnew[j] = xn; xnew[n + j] = yn;
+      }); }
     fam_c_jac(S, nullptr, t2, xnew);                                                     // :144-149
     vec(S, m, [=] __device__(int64_t a, double *) { dcv[a] = t2[a] - cval[a]; cval[a] = t2[a]; });
     // Good Broyden (:156-160): t2 = D' delta ; t1 = delta - D dc ; D += t1 t2' / (t2.dc)
@@ -450,7 +603,7 @@ static int retract_nr(lfpsqp_ctx *c, LargeState &S, int *flag_out, int *it1) {
 // ------------------------------------------------------------------ exact_linesearch! (linesearch.jl:107-339), host control flow
 static int exact_linesearch(lfpsqp_ctx *c, LargeState &S, int kind, double fval, double *newf_o, double *f_diff_o,
                             double *step_diff_o, int *flag_o) {
-  const int64_t n = S.n_loc;
+  const int64_t n = S.nv;
   const lfpsqp_params &prm = S.prm;
   const double phi1 = (3.0 - sqrt(5.0)) / 2.0, phi2 = (sqrt(5.0) - 1.0) / 2.0, phi3 = (sqrt(5.0) + 1.0) / 2.0;
   double Delta = prm.alpha, f_a = 0, f_b = 0, f_c = 0, f_d = 0, a_a = 0, a_b = 0, a_c = 0, a_d = 0;
@@ -462,6 +615,7 @@ static int exact_linesearch(lfpsqp_ctx *c, LargeState &S, int kind, double fval,
     vec(S, n, [=] __device__(int64_t i, double *) { xtil[i] = x[i] + al * d[i]; });
     int i1 = 0, i2 = 0;
     if (kind == 0) { cudaMemcpyAsync(xnew, xtil, n * 8, cudaMemcpyDeviceToDevice, S.stream); flag = 0; }
+    else if (kind == 1) { cudaMemcpyAsync(xnew, xtil, n * 8, cudaMemcpyDeviceToDevice, S.stream); y_retract(S, xnew, x); flag = 0; }
     else if (kind == 2) rc |= retract_nr(c, S, &flag, &i1);
     else rc |= retract_pp(c, S, &flag, &i1, &i2);
     S.retract_outer += i1; S.retract_pcg += i2; S.armijo_trials++;
@@ -469,7 +623,7 @@ static int exact_linesearch(lfpsqp_ctx *c, LargeState &S, int kind, double fval,
   };
   auto FVAL = [&](const double *pt) -> double {
     fam_f(S, pt); finalize(S, 1u, 0);
-    if (read_ctrl(c, S)) { rc = -1; return NAN; }
+    if (read_ctrl(c, S) || S.cb_err) { rc = -1; return NAN; }
     return S.hctrl->s[0];
   };
   cudaMemcpyAsync(x_d, x, n * 8, cudaMemcpyDeviceToDevice, S.stream); f_d = fval;
@@ -529,21 +683,29 @@ static int exact_linesearch(lfpsqp_ctx *c, LargeState &S, int kind, double fval,
   double newf;
   if (f_b < f_c) { cudaMemcpyAsync(xnew, x_b, n * 8, cudaMemcpyDeviceToDevice, S.stream); newf = f_b; }
   else { cudaMemcpyAsync(xnew, x_c, n * 8, cudaMemcpyDeviceToDevice, S.stream); newf = f_c; }
-  vec(S, n, [=] __device__(int64_t i, double *acc) { double t = xnew[i] - x[i]; acc[0] += t * t; }, 0, 1);
+  vec(S, S.n_loc, [=] __device__(int64_t i, double *acc) { double t = xnew[i] - x[i]; acc[0] += t * t; }, 0, 1);   // first n entries
   finalize(S, 1u, 0);
   if (read_ctrl(c, S)) return -1;
   *step_diff_o = sqrt(S.hctrl->s[0]); *f_diff_o = fabs(newf - fval); *newf_o = newf; *flag_o = flag;
   return 0;
 }
 
-// ------------------------------------------------------------------ the driver (optimize.jl:119-443, no bounds)
+// ------------------------------------------------------------------ the driver (optimize.jl:119-443)
 static int solve(lfpsqp_ctx *c, LargeState &S, const double *x0_host, double *x_out, double *obj_hist, int64_t H,
                  int64_t *obj_len, double *lambda, lfpsqp_term *term, lfpsqp_stats *stats) {
-  const int64_t n = S.n_loc; const int m = S.m;
+  const int64_t n = S.n_loc, nv = S.nv; const int m = S.m;
+  const bool ineq = S.ineq; const lfpsqp::IneqDev I = S.I;
   const lfpsqp_params &prm = S.prm;
   double *x = S.x, *g = S.g, *d = S.d, *xnew = S.xnew, *xtil = S.xtil, *nd = S.nd;
   S.reset_counters();
+  S.cb_err = 0;
   CK(cudaMemcpyAsync(x, x0_host, n * sizeof(double), cudaMemcpyHostToDevice, S.stream));
+  CK(cudaMemsetAsync(g, 0, nv * sizeof(double), S.stream));                              // g[n+1:] == 0 (optimize.jl:191)
+  if (m > 0) CK(cudaMemsetAsync(S.cvc, 0, m * sizeof(double), S.stream));
+  if (ineq) {                                                                            // x = [x0 ; y0] (optimize.jl:176-182)
+    vec(S, n, [=] __device__(int64_t j, double *) { x[n + j] = ineq_y0(I.q[j], I.r[j], I.s[j], I.t[j], x[j]); });
+    CK(cudaMemsetAsync(S.cvh, 0, n * sizeof(double), S.stream));
+  }
   memset(S.hctrl, 0, sizeof(LargeCtrl));
   write_ctrl_fields(S);
   int64_t it = 0, nobj = 0;
@@ -551,25 +713,38 @@ static int solve(lfpsqp_ctx *c, LargeState &S, const double *x0_host, double *x_
   fam_f(S, x); finalize(S, 1u, 0);
   if (m > 0) fam_c_jac(S, nullptr, S.cval, x);                                          // :252
   if (read_ctrl(c, S)) return LFPSQP_ERR_CUDA;
+  if (S.cb_err) return LFPSQP_ERR_CALLBACK;
   double fval = S.hctrl->s[0];
   if (nobj < H) obj_hist[nobj] = fval;
   nobj++;
   int cond = LFPSQP_F_TOL, status = 0, last_flag = 0;
   while (true) {
     fam_grad(S, g, x);                                                                  // :259
-    vec(S, n, [=] __device__(int64_t i, double *) { d[i] = -1.0 * g[i]; });              // :262
+    vec(S, nv, [=] __device__(int64_t i, double *) { d[i] = -1.0 * g[i]; });             // :262
     S.launches++;
-    if (m > 0) {
+    if (prm.beta > 0) {                                                                 // :264-273, randn! from the caller's RNG
+      if (S.cb.randn(S.cb.user, S.hw, nv)) S.cb_err = 1;
+      double *noise = S.w0;
+      CK(cudaMemcpyAsync(noise, S.hw, nv * sizeof(double), cudaMemcpyHostToDevice, S.stream));
+      const double coef = prm.t_beta > 0 ? prm.beta * fmax(1.0 - (double)it / (double)prm.t_beta, 0.0) : prm.beta;
+      vec(S, nv, [=] __device__(int64_t i, double *) { d[i] += coef * noise[i]; });
+      CK(cudaStreamSynchronize(S.stream));   // S.hw is reused by the next callback
+    }
+    if (ineq) ineq_gradient(S, x);                                                      // :277
+    if (m > 0 || ineq) {
       const double tf0 = now_ms();
-      fam_c_jac(S, S.J, S.cval, x);                                                     // :283
-      if (factorize(c, S)) return LFPSQP_ERR_CUDA;
-      project(S, d, S.lam, 0, 1);                                                       // :306-307, :333-343
+      if (m > 0) {
+        fam_c_jac(S, S.J, S.cval, x);                                                   // :283
+        if (factorize(c, S)) return LFPSQP_ERR_CUDA;
+      }
+      project(S, d, S.lam, 0, 1, 1);                                                    // :306-307 / :314-317, :331-343
       S.t_factor_pending = tf0;
     } else {
       vec(S, n, [=] __device__(int64_t i, double *acc) { double r = d[i]; acc[0] += r * r; acc[3] = nanmax(acc[3], fabs(r)); }, 0, 1, 1);
     }
     finalize(S, 1u, 8u);
     if (read_ctrl(c, S)) return LFPSQP_ERR_CUDA;
+    if (S.cb_err) return LFPSQP_ERR_CALLBACK;
     if (S.t_factor_pending > 0) { S.ms_factor += now_ms() - S.t_factor_pending; S.t_factor_pending = 0; }
     if (S.hctrl->rankflag) { status |= LFPSQP_ST_RANK_DEFICIENT; cond = LFPSQP_MAX_ITER; break; }
     kkt_diff = S.hctrl->s[3];                                                           // :320
@@ -584,16 +759,17 @@ static int solve(lfpsqp_ctx *c, LargeState &S, const double *x0_host, double *x_
       prev_grad_norm = gn;
       const double tp0 = now_ms();
       fam_hess_prepare(S, x, S.lam);
-      if (projcg(c, S, tol, prm.tn_maxiter, S.cg_chunk)) return LFPSQP_ERR_CUDA;
+      if (projcg(c, S, tol, prm.tn_maxiter, S.cg_chunk)) return S.cb_err ? LFPSQP_ERR_CALLBACK : LFPSQP_ERR_CUDA;
       S.ms_projcg += now_ms() - tp0;
-      vec(S, n, [=] __device__(int64_t i, double *acc) { acc[0] += nd[i] * d[i]; }, 0, 1);
+      vec(S, nv, [=] __device__(int64_t i, double *acc) { acc[0] += nd[i] * d[i]; }, 0, 1);
       finalize(S, 1u, 0);
       if (read_ctrl(c, S)) return LFPSQP_ERR_CUDA;
-      if (S.hctrl->s[0] > 0.0) { cudaMemcpyAsync(d, nd, n * sizeof(double), cudaMemcpyDeviceToDevice, S.stream); S.newton_accepted++; }
+      if (S.hctrl->s[0] > 0.0) { cudaMemcpyAsync(d, nd, nv * sizeof(double), cudaMemcpyDeviceToDevice, S.stream); S.newton_accepted++; }
     }
-    const int kind = (m > 0) ? ((!prm.do_project_retract) ? 2 : 3) : 0;                 // :396-412 (rank == m here)
+    // :396-412 (rank == m here): NR / ProjPenalty with constraints, else YRetract with bounds, else Euclidean
+    const int kind = (m > 0) ? ((!prm.do_project_retract) ? 2 : 3) : (ineq ? 1 : 0);
     // armijo! (linesearch.jl:32-89)
-    vec(S, n, [=] __device__(int64_t i, double *acc) { acc[0] += d[i] * g[i]; }, 0, 1);
+    vec(S, nv, [=] __device__(int64_t i, double *acc) { acc[0] += d[i] * g[i]; }, 0, 1);
     finalize(S, 1u, 0);
     if (read_ctrl(c, S)) return LFPSQP_ERR_CUDA;
     const double ar_dot = S.hctrl->s[0];
@@ -602,20 +778,22 @@ static int solve(lfpsqp_ctx *c, LargeState &S, const double *x0_host, double *x_
     int flag = 0;
     const double tl0 = now_ms();
     const bool exact = (prm.linesearch != 0 && !prm.disable_linesearch);                // :415-420
-    if (exact) { if (exact_linesearch(c, S, kind, fval, &newf, &f_diff, &step_diff, &flag)) return LFPSQP_ERR_CUDA; }
+    if (exact) { if (exact_linesearch(c, S, kind, fval, &newf, &f_diff, &step_diff, &flag)) return S.cb_err ? LFPSQP_ERR_CALLBACK : LFPSQP_ERR_CUDA; }
     while (!exact && step_diff > prm.eps_x) {
       double al = alpha;
-      vec(S, n, [=] __device__(int64_t i, double *) { xtil[i] = x[i] + al * d[i]; });
+      vec(S, nv, [=] __device__(int64_t i, double *) { xtil[i] = x[i] + al * d[i]; });
       int i1 = 0, i2 = 0;
-      if (kind == 0) cudaMemcpyAsync(xnew, xtil, n * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);
-      else if (kind == 2) { if (retract_nr(c, S, &flag, &i1)) return LFPSQP_ERR_CUDA; }
-      else { if (retract_pp(c, S, &flag, &i1, &i2)) return LFPSQP_ERR_CUDA; }
+      if (kind == 0) cudaMemcpyAsync(xnew, xtil, nv * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);
+      else if (kind == 1) { cudaMemcpyAsync(xnew, xtil, nv * sizeof(double), cudaMemcpyDeviceToDevice, S.stream); y_retract(S, xnew, x); }
+      else if (kind == 2) { if (retract_nr(c, S, &flag, &i1)) return S.cb_err ? LFPSQP_ERR_CALLBACK : LFPSQP_ERR_CUDA; }
+      else { if (retract_pp(c, S, &flag, &i1, &i2)) return S.cb_err ? LFPSQP_ERR_CALLBACK : LFPSQP_ERR_CUDA; }
       S.retract_outer += i1; S.retract_pcg += i2; S.armijo_trials++;
       if (flag > 0) { alpha *= prm.s; continue; }                                       // :57-60
       fam_f(S, xnew);
       vec(S, n, [=] __device__(int64_t i, double *acc) { double t = xnew[i] - x[i]; acc[0] += t * t; }, 1, 1);   // slot 1 only
       finalize(S, 3u, 0);
       if (read_ctrl(c, S)) return LFPSQP_ERR_CUDA;
+      if (S.cb_err) return LFPSQP_ERR_CALLBACK;
       newf = S.hctrl->s[0];
       step_diff = sqrt(S.hctrl->s[1]);
       f_diff = fabs(newf - fval);
@@ -626,11 +804,16 @@ static int solve(lfpsqp_ctx *c, LargeState &S, const double *x0_host, double *x_
     }
     last_flag = flag;
     S.ms_linesearch += now_ms() - tl0;
-    cudaMemcpyAsync(x, xnew, n * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);    // :424
+    cudaMemcpyAsync(x, xnew, nv * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);   // :424
     fval = newf;
     if (nobj < H) obj_hist[nobj] = fval;
     nobj++;
     it++;
+    if (S.cb.callback && prm.callback_period > 0 && it % prm.callback_period == 0) {   // :432-434, param.callback(i, x)
+      CK(cudaMemcpyAsync(S.hw, x, nv * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+      CK(cudaStreamSynchronize(S.stream));
+      if (S.cb.callback(S.cb.user, it, S.hw, nv)) return LFPSQP_ERR_CALLBACK;
+    }
   }
   CK(cudaMemcpyAsync(x_out, x, n * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
   if (m > 0) CK(cudaMemcpyAsync(lambda, S.lam, m * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
@@ -655,6 +838,7 @@ void lfpsqp_large_release(lfpsqp_ctx *c) {
   cudaSetDevice(c->device);
   for (void *p : S->owned) cudaFree(p);
   if (S->hctrl) cudaFreeHost(S->hctrl);
+  for (double *p : {S->hx, S->hv, S->hw, S->hlam, S->hc, S->hJ}) if (p) cudaFreeHost(p);
   if (S->ev_g0) cudaEventDestroy(S->ev_g0);
   if (S->ev_g1) cudaEventDestroy(S->ev_g1);
   comm_release(*S);
@@ -673,20 +857,26 @@ extern "C" int lfpsqp_large_setup(lfpsqp_ctx *c, int family, int64_t n_global, i
                                   const double *params, int params_on_device) {
   if (!c) return LFPSQP_ERR_ARG;
   cudaSetDevice(c->device);
-  if (family != LFPSQP_FAM_DIAGQUAD && family != LFPSQP_FAM_THOMSON)
-    return c->fail(LFPSQP_ERR_FAMILY, "large-n mode supports the DIAGQUAD and THOMSON families");
+  if (family != LFPSQP_FAM_DIAGQUAD && family != LFPSQP_FAM_THOMSON && family != LFPSQP_FAM_HOST)
+    return c->fail(LFPSQP_ERR_FAMILY, "large-n mode supports the DIAGQUAD, THOMSON and HOST (callback) families");
   if (n_global < 1 || m < 0 || n_loc < 1 || col0 < 0 || col0 + n_loc > n_global || m > n_global)
     return c->fail(LFPSQP_ERR_ARG, "bad sizes for large-n setup");
   if (c->comm.world <= 1 && n_loc != n_global) return c->fail(LFPSQP_ERR_ARG, "a column shard needs a communicator (lfpsqp_comm_init)");
   if (family == LFPSQP_FAM_THOMSON && (n_global % 3 || m != n_global / 3 || n_loc != n_global))
     return c->fail(LFPSQP_ERR_FAMILY, "THOMSON needs n = 3 m and runs on one GPU (its callbacks need all of x)");
   if (m > 16384) return c->fail(LFPSQP_ERR_ARG, "m too large for the replicated factor");
+  if (family == LFPSQP_FAM_HOST) {
+    const lfpsqp_host_callbacks *cb = (const lfpsqp_host_callbacks *)params;
+    if (!cb || !cb->f || !cb->grad || !cb->hess_lag_vec || (m > 0 && (!cb->c || !cb->jac)))
+      return c->fail(LFPSQP_ERR_ARG, "HOST family: f, grad, hess_lag_vec (and c, jac when m > 0) callbacks are required");
+    if (n_loc != n_global || c->comm.world > 1) return c->fail(LFPSQP_ERR_FAMILY, "the HOST (callback) family runs on one GPU");
+  }
   lfpsqp_large_release(c);
   LargeState *Sp = new LargeState(); LargeState &S = *Sp;
   c->large = Sp;
   S.comm = &c->comm; S.world = c->comm.world > 1 ? c->comm.world : 1; S.rank = c->comm.rank;
   if (S.world > 1 && family == LFPSQP_FAM_THOMSON) return c->fail(LFPSQP_ERR_FAMILY, "THOMSON is single-GPU");
-  S.family = family; S.n = n_global; S.n_loc = n_loc; S.col0 = col0; S.m = (int)m; S.stream = c->stream;
+  S.family = family; S.n = n_global; S.n_loc = n_loc; S.nv = n_loc; S.col0 = col0; S.m = (int)m; S.stream = c->stream;
   S.sm_count = c->sm_count; S.ldj = up2(n_loc); S.ldm = up2(std::max<int64_t>(m, 1));
   S.vgrid = (int)std::min<int64_t>(std::max<int64_t>((n_loc + 255) / 256, 1), std::min<int64_t>(MAXP, 4 * (int64_t)c->sm_count));
   S.np_loop_raw = S.vgrid; S.np_loop = (S.world > 1) ? 1 : S.vgrid;
@@ -708,19 +898,28 @@ extern "C" int lfpsqp_large_setup(lfpsqp_ctx *c, int family, int64_t n_global, i
   S.gemm_ws_bytes = std::max<size_t>((size_t)16 * mm * 64 * 8, std::min<size_t>(mm * mm * 8 * 8, (size_t)256 << 20));
   { char *ws = nullptr; ok &= dalloc(S, &ws, S.gemm_ws_bytes); S.gemm_ws = (double *)ws; }
   double **vecs[] = {&S.x, &S.xnew, &S.xtil, &S.g, &S.d, &S.nd, &S.w0, &S.w1, &S.w2, &S.w3, &S.w4, &S.hdiag};
-  for (double **v : vecs) ok &= dalloc(S, v, nl + 2);
-  double **mv[] = {&S.cval, &S.lam, &S.tm, &S.ty, &S.tu, &S.nr_t1, &S.nr_t2, &S.nr_dc};
+  for (double **v : vecs) ok &= dalloc(S, v, 2 * nl + 2);   // [x-half | y-half] when bounds are set later
+  double **mv[] = {&S.cval, &S.lam, &S.tm, &S.ty, &S.tu, &S.nr_t1, &S.nr_t2, &S.nr_dc, &S.cvc};
   for (double **v : mv) ok &= dalloc(S, v, mm + 2);
   ok &= dalloc(S, &S.cpart, (size_t)S.nsplit * std::max(nl, mm) + 2);
   ok &= dalloc(S, &S.lp, (size_t)NSLOT * MAXP); ok &= dalloc(S, &S.gpart, (size_t)NSLOT * MAXP);
   ok &= dalloc(S, &S.ctrl, 1); ok &= dalloc(S, &S.commbuf, 64);
   if (family == LFPSQP_FAM_THOMSON) ok &= dalloc(S, &S.pairws, (size_t)16 * nl + 2);
   S.Dnr = nullptr;
+  if (family == LFPSQP_FAM_HOST) {
+    S.cb = *(const lfpsqp_host_callbacks *)params;
+    ok &= dalloc(S, &S.Jstage, mm * nl);
+    bool hok = cudaMallocHost((void **)&S.hx, (nl + 2) * 8) == cudaSuccess && cudaMallocHost((void **)&S.hv, (2 * nl + 2) * 8) == cudaSuccess &&
+               cudaMallocHost((void **)&S.hw, (2 * nl + 2) * 8) == cudaSuccess && cudaMallocHost((void **)&S.hlam, (mm + 2) * 8) == cudaSuccess &&
+               cudaMallocHost((void **)&S.hc, (mm + 2) * 8) == cudaSuccess && cudaMallocHost((void **)&S.hJ, mm * nl * 8) == cudaSuccess;
+    if (!hok) { cudaGetLastError(); ok = false; }
+  }
   if (!ok) { lfpsqp_large_release(c); return c->fail(LFPSQP_ERR_NOMEM, "large-n setup: device allocation failed"); }
   if (cudaMallocHost((void **)&S.hctrl, sizeof(LargeCtrl)) != cudaSuccess) { lfpsqp_large_release(c); return c->fail(LFPSQP_ERR_NOMEM, "pinned allocation failed"); }
   cudaEventCreate(&S.ev_g0); cudaEventCreate(&S.ev_g1);
   cudaMemsetAsync(S.lp, 0, (size_t)NSLOT * MAXP * 8, S.stream); cudaMemsetAsync(S.gpart, 0, (size_t)NSLOT * MAXP * 8, S.stream);
   cudaMemsetAsync(S.ctrl, 0, sizeof(LargeCtrl), S.stream);
+  cudaMemsetAsync(S.J, 0, mm * S.ldj * sizeof(double), S.stream);   // the pad column of an odd n_loc must stay zero (16-byte K chunks)
   // parameters
   if (family == LFPSQP_FAM_DIAGQUAD) {
     const size_t cnt = 2 * mm * nl * (m > 0 ? 1 : 0) + (size_t)m + 2 * nl;
@@ -752,10 +951,11 @@ static int need_large(lfpsqp_ctx *c) {
 }
 static int prep_params(lfpsqp_ctx *c, LargeState &S, const lfpsqp_params *prm) {
   if (!prm) return c->fail(LFPSQP_ERR_ARG, "params is NULL");
-  if (prm->beta > 0) return c->fail(LFPSQP_ERR_UNSUPPORTED, "beta>0 is not supported on the device path");
+  if (prm->beta > 0 && !S.cb.randn)
+    return c->fail(LFPSQP_ERR_UNSUPPORTED, "beta>0 needs the randn host callback (LFPSQP_FAM_HOST): the noise must come from the caller's RNG stream");
   S.prm = *prm;
   if (prm->linesearch != 0 && !prm->disable_linesearch && !S.ex[0]) {
-    for (int i = 0; i < 4; i++) if (!dalloc(S, &S.ex[i], (size_t)S.n_loc + 2)) return c->fail(LFPSQP_ERR_NOMEM, "exact line search workspace allocation failed");
+    for (int i = 0; i < 4; i++) if (!dalloc(S, &S.ex[i], 2 * (size_t)S.n_loc + 2)) return c->fail(LFPSQP_ERR_NOMEM, "exact line search workspace allocation failed");
   }
   if (!prm->do_project_retract && S.m > 0 && !S.Dnr) {
     if (!dalloc(S, &S.Dnr, (size_t)S.m * S.ldm)) return c->fail(LFPSQP_ERR_NOMEM, "NR workspace allocation failed");
@@ -779,23 +979,68 @@ extern "C" int lfpsqp_large_solve(lfpsqp_ctx *c, const double *x0_loc, const lfp
   return LFPSQP_OK;
 }
 
+int build_bounds_public(int64_t n, int64_t p, const double *xl, const double *xu, std::vector<double> &bnd);  // abi.cu
+
+// Bounds of this rank's entries: InequalityData (src/inequality_helper.jl:39-85) + the workspaces of the 2n embedding.
+extern "C" int lfpsqp_large_set_bounds(lfpsqp_ctx *c, const double *xl_loc, const double *xu_loc) {
+  int rc = need_large(c); if (rc) return rc;
+  LargeState &S = *c->large;
+  const int64_t nl = S.n_loc;
+  std::vector<double> bnd;
+  int ineq = build_bounds_public(nl, 0, xl_loc, xu_loc, bnd);
+  if (ineq == LFPSQP_ERR_BOUNDS) return c->fail(LFPSQP_ERR_BOUNDS, "Infeasible: lower bounds cannot be greater than upper bounds");
+  if (ineq < 0) return c->fail(LFPSQP_ERR_ARG, "xl and xu must both be given or both be NULL");
+  if (S.world > 1) {  // optimize.jl:151 looks at ALL of xl, xu: any rank with a finite bound switches every rank
+    double flag = ineq ? 1.0 : 0.0;
+    CK(cudaMemcpyAsync(S.commbuf, &flag, 8, cudaMemcpyHostToDevice, S.stream));
+    comm_allreduce(S, S.commbuf, 1);
+    CK(cudaMemcpyAsync(&flag, S.commbuf, 8, cudaMemcpyDeviceToHost, S.stream));
+    CK(cudaStreamSynchronize(S.stream));
+    if (flag > 0 && !ineq) bnd.assign(5 * nl, 0.0);   // this shard: all lines (q = r = s = t = 0)
+    ineq = flag > 0;
+  }
+  S.ineq = ineq != 0;
+  S.nv = S.ineq ? 2 * nl : nl;
+  if (!S.ineq) { S.I = lfpsqp::IneqDev(); return LFPSQP_OK; }
+  if (!S.bq) {
+    bool ok = true;
+    double **nvv[] = {&S.bq, &S.br, &S.bs, &S.bt, &S.I.Dx, &S.I.Dy, &S.I.S, &S.I.lamy, &S.cvh, &S.pb};
+    for (double **v : nvv) ok &= dalloc(S, v, (size_t)nl + 2);
+    if (S.m > 0) { ok &= dalloc(S, &S.Jw, (size_t)S.m * S.ldj); if (ok) cudaMemsetAsync(S.Jw, 0, (size_t)S.m * S.ldj * 8, S.stream); }
+    if (!ok) return c->fail(LFPSQP_ERR_NOMEM, "bound-embedding workspace allocation failed");
+  }
+  // bnd layout (abi.cu build_bounds): [kind | q | r | s | t], each nl doubles
+  CK(cudaMemcpyAsync(S.bq, bnd.data() + nl, nl * 8, cudaMemcpyHostToDevice, S.stream));
+  CK(cudaMemcpyAsync(S.br, bnd.data() + 2 * nl, nl * 8, cudaMemcpyHostToDevice, S.stream));
+  CK(cudaMemcpyAsync(S.bs, bnd.data() + 3 * nl, nl * 8, cudaMemcpyHostToDevice, S.stream));
+  CK(cudaMemcpyAsync(S.bt, bnd.data() + 4 * nl, nl * 8, cudaMemcpyHostToDevice, S.stream));
+  CK(cudaMemsetAsync(S.I.lamy, 0, nl * 8, S.stream));
+  CK(cudaStreamSynchronize(S.stream));   // bnd is a stack-owned host vector
+  S.I.q = S.bq; S.I.r = S.br; S.I.s = S.bs; S.I.t = S.bt; S.I.nx = nl;
+  return LFPSQP_OK;
+}
+
 // optimize(...) for one large instance on one GPU with host-resident family parameters
 extern "C" int lfpsqp_solve_large(lfpsqp_ctx *c, int family, int64_t n, int64_t m, const double *fam_params,
                                   const double *x0, const double *xl, const double *xu, const lfpsqp_params *prm,
                                   double *x_out, double *obj_hist, int64_t H, int64_t *obj_len, double *lambda,
                                   lfpsqp_term *term, lfpsqp_stats *stats) {
   if (!c) return LFPSQP_ERR_ARG;
-  if (xl || xu) {
-    if (!xl || !xu) return c->fail(LFPSQP_ERR_ARG, "xl and xu must both be given or both be NULL");
-    for (int64_t i = 0; i < n; i++) {
-      if (xl[i] > xu[i]) return c->fail(LFPSQP_ERR_BOUNDS, "Infeasible: lower bounds cannot be greater than upper bounds");
-      if (!(xl[i] == -INFINITY && xu[i] == INFINITY))
-        return c->fail(LFPSQP_ERR_UNSUPPORTED, "finite bounds are not supported in large-n mode yet (use batched mode)");
-    }
-  }
   int rc = lfpsqp_large_setup(c, family, n, m, 0, n, fam_params, 0);
   if (rc) return rc;
+  rc = lfpsqp_large_set_bounds(c, xl, xu);
+  if (rc) return rc;
   return lfpsqp_large_solve(c, x0, prm, x_out, obj_hist, H, obj_len, lambda, term, stats);
+}
+
+// The explicit-derivative core optimize(f, grad!, c!, jac!, hess_lag_vec!, x0, xl, xu, m, param) (src/optimize.jl:119-443) for
+// an arbitrary problem whose callbacks run on the host; all linear algebra of the hot path runs on the device.
+extern "C" int lfpsqp_solve_host(lfpsqp_ctx *c, const lfpsqp_host_callbacks *cb, int64_t n, int64_t m, const double *x0,
+                                 const double *xl, const double *xu, const lfpsqp_params *prm, double *x_out,
+                                 double *obj_hist, int64_t H, int64_t *obj_len, double *lambda, lfpsqp_term *term,
+                                 lfpsqp_stats *stats) {
+  return lfpsqp_solve_large(c, LFPSQP_FAM_HOST, n, m, (const double *)cb, x0, xl, xu, prm, x_out, obj_hist, H, obj_len, lambda,
+                            term, stats);
 }
 
 // Unit-level: factorisation of the Jacobian at x (ksvd! replacement) -- G = J J' (lower), L, L^-1 returned to the host
@@ -803,6 +1048,7 @@ extern "C" int lfpsqp_large_factor(lfpsqp_ctx *c, const double *x_loc, double *G
                                    int *rank_deficient, double *gram_ms) {
   int rc = need_large(c); if (rc) return rc;
   LargeState &S = *c->large;
+  if (S.ineq) return c->fail(LFPSQP_ERR_UNSUPPORTED, "unit-level large-n ops work on the unbounded problem (lfpsqp_ineq_op covers the bound operators)");
   lfpsqp_params p; lfpsqp_default_params(&p); S.prm = p;
   const int m = S.m; const size_t ldm = S.ldm;
   CK(cudaMemcpyAsync(S.x, x_loc, S.n_loc * 8, cudaMemcpyHostToDevice, S.stream));
@@ -828,6 +1074,7 @@ extern "C" int lfpsqp_large_factor(lfpsqp_ctx *c, const double *x_loc, double *G
 extern "C" int lfpsqp_large_project(lfpsqp_ctx *c, const double *v_loc, double *v_out_loc, double *lambda_out) {
   int rc = need_large(c); if (rc) return rc;
   LargeState &S = *c->large;
+  if (S.ineq) return c->fail(LFPSQP_ERR_UNSUPPORTED, "unit-level large-n ops work on the unbounded problem (lfpsqp_ineq_op covers the bound operators)");
   CK(cudaMemcpyAsync(S.d, v_loc, S.n_loc * 8, cudaMemcpyHostToDevice, S.stream));
   project(S, S.d, S.lam, 0, 0);
   CK(cudaMemcpyAsync(v_out_loc, S.d, S.n_loc * 8, cudaMemcpyDeviceToHost, S.stream));
@@ -843,6 +1090,7 @@ extern "C" int lfpsqp_large_projcg(lfpsqp_ctx *c, const double *x_loc, const dou
                                    int chunk, double *sol_out_loc, int64_t *iters, double *nr, int *status, double *ms) {
   int rc = need_large(c); if (rc) return rc;
   LargeState &S = *c->large;
+  if (S.ineq) return c->fail(LFPSQP_ERR_UNSUPPORTED, "unit-level large-n ops work on the unbounded problem (lfpsqp_ineq_op covers the bound operators)");
   const int64_t n = S.n_loc;
   double *g = S.g, *d = S.d;
   CK(cudaMemcpyAsync(S.x, x_loc, n * 8, cudaMemcpyHostToDevice, S.stream));
@@ -874,6 +1122,7 @@ extern "C" int lfpsqp_large_retract(lfpsqp_ctx *c, int method, const double *x_b
                                     int64_t *iters, int64_t *pcg_iters) {
   int rc = need_large(c); if (rc) return rc;
   LargeState &S = *c->large;
+  if (S.ineq) return c->fail(LFPSQP_ERR_UNSUPPORTED, "unit-level large-n ops work on the unbounded problem (lfpsqp_ineq_op covers the bound operators)");
   lfpsqp_params p2 = *prm; p2.do_project_retract = (method == 0) ? 0 : 1;
   rc = prep_params(c, S, &p2); if (rc) return rc;
   if (S.m < 1) return c->fail(LFPSQP_ERR_ARG, "retraction needs m > 0");
@@ -901,6 +1150,7 @@ extern "C" int lfpsqp_large_pcg(lfpsqp_ctx *c, const double *x_point_loc, double
                                 int64_t maxiter, double *x_out_loc, double *r_out_loc, int *flag, int64_t *iters) {
   int rc = need_large(c); if (rc) return rc;
   LargeState &S = *c->large;
+  if (S.ineq) return c->fail(LFPSQP_ERR_UNSUPPORTED, "unit-level large-n ops work on the unbounded problem (lfpsqp_ineq_op covers the bound operators)");
   if (S.m < 1) return c->fail(LFPSQP_ERR_ARG, "pcg needs m > 0");
   const int64_t n = S.n_loc;
   double *r = S.w0, *pv = S.w1, *dx = S.w3, *lp = S.lp;

@@ -16,4 +16,11 @@ struct LargeCtrl {
   int rankflag, pad;
 };
 
+// bound embedding of the large-n mode (kernels in large_ineq.cuh); device arrays, each nx doubles
+struct IneqDev {
+  const double *q = nullptr, *r = nullptr, *s = nullptr, *t = nullptr;   // InequalityData (inequality_helper.jl:1-8, :54-82)
+  double *Dx = nullptr, *Dy = nullptr, *S = nullptr, *lamy = nullptr;   // inequality_gradient! output, lambda_y
+  int64_t nx = 0;
+};
+
 }  // namespace lfpsqp

@@ -10,6 +10,17 @@
 struct LargeState {
   int family = 0;
   int64_t n = 0, n_loc = 0, col0 = 0, ldj = 0, ldm = 0;
+  // bound embedding (src/inequality_helper.jl): working vectors are [x-half | y-half], nv = 2 n_loc entries per rank
+  bool ineq = false;
+  int64_t nv = 0;
+  lfpsqp::IneqDev I;
+  double *bq = nullptr, *br = nullptr, *bs = nullptr, *bt = nullptr;   // InequalityData (owned copies behind I.q .. I.t)
+  double *cvh = nullptr, *cvc = nullptr;   // cvalaug = [h ; c] of ProjPenalty (retractions.jl:29), persistent across calls
+  double *pb = nullptr, *Jw = nullptr;     // x-half operand of PJct' v ; J diag(Dy) for the weighted Gram
+  // host-callback family (LFPSQP_FAM_HOST): the callbacks, pinned staging buffers, device staging of Jc (n x m)
+  lfpsqp_host_callbacks cb = {};
+  double *hx = nullptr, *hv = nullptr, *hw = nullptr, *hlam = nullptr, *hc = nullptr, *hJ = nullptr, *Jstage = nullptr;
+  int cb_err = 0;
   int m = 0, sm_count = 148, world = 1, rank = 0;
   cudaStream_t stream = nullptr;
   lfpsqp_params prm;

@@ -23,6 +23,14 @@ class LargeProblem:
             pp, on_dev = _lib.ptr(fam.params), 0
         self.ctx.check(self.ctx.lib.lfpsqp_large_setup(self.ctx.h, fam.id, self.n, self.m, col0, self.n_loc, pp, on_dev))
 
+    def set_bounds(self, xl, xu):
+        """xl <= x <= xu for this rank's entries (None, None = no bounds): the 2n embedding of src/inequality_helper.jl"""
+        xl = None if xl is None else np.ascontiguousarray(xl, dtype=np.float64)
+        xu = None if xu is None else np.ascontiguousarray(xu, dtype=np.float64)
+        if xl is not None and xu is not None and not (len(xl) == len(xu) == self.n_loc):
+            raise _lib.LFPSQPError("xl, xu, and x0 must all be the same length")     # optimize.jl:144-148
+        self.ctx.check(self.ctx.lib.lfpsqp_large_set_bounds(self.ctx.h, _lib.ptr(xl), _lib.ptr(xu)))
+
     def solve(self, x0, param=None, history=4096, return_stats=False):
         param = param or LFPSQPParams()
         cp = param.to_c()
