@@ -56,7 +56,8 @@ enum { LFPSQP_F_TOL = 0, LFPSQP_X_TOL = 1, LFPSQP_KKT_TOL = 2, LFPSQP_MAX_ITER =
 #define LFPSQP_ST_RANK_DEFICIENT 1 /* the projected Jacobian lost rank at some iterate. Batched mode: informational -- the
                                       truncated path of optimize.jl:297-302 was taken (eigen-decomposition of J W J',
                                       pseudo-inverse); large-n mode: the solve stopped at that iterate */
-#define LFPSQP_ST_NONFINITE 2
+#define LFPSQP_ST_NONFINITE 2      /* a non-finite iterate, or the retraction failed at every step length down to alpha < 1e-100
+                                      (flag_last = 98; the reference spins forever there, src/linesearch.jl:57-60) */
 
 /* TerminationInfo, src/LFPSQP.jl:45-51 : {Int32 enum, 3 x Float64, Int64}; the enum's padding carries status */
 typedef struct {

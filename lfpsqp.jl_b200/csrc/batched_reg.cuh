@@ -590,7 +590,10 @@ struct RegSolver {
         else if (kind == 2) flag = retract_nr(xnew, xtil, &i1);
         else flag = retract_pp(xnew, xtil, &i1, &i2);
         st_rout += i1; st_rpcg += i2; st_trials++;
-        if (flag > 0) { alpha *= prm.s; continue; }
+        // linesearch.jl:57-60 has no lower bound on alpha in this branch: when the retraction fails at EVERY alpha the
+        // reference spins forever once alpha has underflowed to 0.  Stop at the floor the other branch uses (:82-85):
+        // flag 98, LFPSQP_ST_NONFINITE.
+        if (flag > 0) { if (alpha < 1e-100) { flag = 98; break; } alpha *= prm.s; continue; }
         newf = f_aux(xnew);
         double s2 = 0.0;
         LF_UNROLL for (int s = 0; s < NPL; s++) { double t = xnew.x[s] - x.x[s]; s2 += t * t; }   // first n_A entries (:66)
@@ -602,6 +605,7 @@ struct RegSolver {
         if (alpha < 1e-100) { flag = 99; break; }
       }
       last_flag = flag;
+      if (flag == 98) { status |= LFPSQP_ST_NONFINITE; cond = LFPSQP_MAX_ITER; break; }
       x = xnew;
       fval = newf;
       if (lane == 0 && nobj < A.H) A.obj_hist[k * A.H + nobj] = fval;

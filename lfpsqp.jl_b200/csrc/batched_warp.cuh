@@ -611,7 +611,10 @@ struct Solver {
       int i1, i2;
       flag = retract(kind, &i1, &i2);
       st.armijo_trials++;
-      if (flag > 0) { alpha *= prm.s; continue; }                         // :57-60
+      // linesearch.jl:57-60 has no lower bound on alpha in this branch: when the retraction fails at EVERY alpha the
+      // reference spins forever once alpha has underflowed to 0.  Stop at the floor the other branch uses (:82-85):
+        // flag 98, LFPSQP_ST_NONFINITE.
+      if (flag > 0) { if (alpha < 1e-100) { flag = 98; break; } alpha *= prm.s; continue; }   // :57-60
       newf = f_aux(xnew);
       double s = 0;
       for (int k = g.lane; k < NA; k += G::SIZE) { double t = xnew[k] - x[k]; s += t * t; }   // :66 first n entries
@@ -754,6 +757,7 @@ struct Solver {
       if (prm.linesearch == 0 || prm.disable_linesearch) flag = armijo(kind, fval, &newf, &f_diff, &step_diff);
       else flag = exact_linesearch(kind, fval, &newf, &f_diff, &step_diff);
       st.flag_last = flag;
+      if (flag == 98) { status |= LFPSQP_ST_NONFINITE; cond = LFPSQP_MAX_ITER; break; }
       copy(x, xnew, N);                                                    // :424-426
       fval = newf;
       if (g.lane == 0 && nobj < A.H) A.obj_hist[k * A.H + nobj] = fval;

@@ -95,9 +95,7 @@ void ar(LargeState &S, double *buf, size_t count, int op) {
 // order through the mapped peer pointers (remote loads) -- the same order everywhere, so every rank gets the
 // bitwise-identical result.  A region is reused two calls later; a peer's flag for call e+1 implies that its reads of
 // call e are complete (stream order), so the parity double buffer is race-free.
-constexpr int PC_MAX = 8192, PC_SCAL = 32, PC_RANKS = 8, PC_COLS = 16;
-constexpr size_t PC_DATA = 2 * (size_t)(PC_MAX + PC_SCAL);
-constexpr size_t PC_REGION_BYTES = PC_DATA * 8 + (size_t)PC_RANKS * PC_COLS * 8;
+// (layout constants PC_* / FZ_* live in large_ctrl.h: the fused projcg kernel shares the exported region)
 
 struct PeerPtrs { double *r[PC_RANKS]; };
 

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <chrono>
@@ -69,6 +70,16 @@ static void gemm_nt(LargeState &S, int M, int N, int K, const double *A, int64_t
     ksplit = std::min(std::min(16, S.sm_count / tiles), K / 256);
     while (ksplit > 1 && (size_t)ksplit * M * N * 8 > S.gemm_ws_bytes) ksplit--;
     if (ksplit < 1) ksplit = 1;
+  } else if (mode == GEMM_ASSIGN && lower && K >= 8192 && tiles < 8 * S.sm_count) {
+    // wave quantisation of the big SYRK (C5: 136 lower tiles on 148 SMs = one wave at 92 %; C4: 528 tiles = 3.57 waves):
+    // split K so that tiles x ksplit fills whole waves (C5: 13 -> 1768 CTAs = 11.95 waves)
+    auto eff = [&](int ks) { int64_t w = (int64_t)tiles * ks; return (double)w / (double)(((w + S.sm_count - 1) / S.sm_count) * S.sm_count); };
+    int best = 1;
+    for (int ks = 2; ks <= 16; ks++) {
+      if ((size_t)ks * M * N * 8 > S.gemm_ws_bytes || K / ks < 2048) break;
+      if (eff(ks) > eff(best) + 0.02) best = ks;
+    }
+    ksplit = best;
   }
   if (ksplit == 1) {
     if (narrow) dgemm_nt_kernel<64><<<grid, 256, dgemm_smem_bytes<64>(), S.stream>>>(M, N, K, A, lda, B, ldb, C, ldc, mode, lower, 1, 0);
@@ -378,7 +389,17 @@ static int projcg(lfpsqp_ctx *c, LargeState &S, double tol, int64_t maxit, int c
   S.hctrl->nr = INFINITY;
   write_ctrl_fields(S);
   int64_t k = 0;
-  while (S.hctrl->status == 0) {
+  // persistent fused path (large_fused.cu): one cooperative kernel per chunk instead of 8 launches per iteration
+  bool fused = S.fused_ok && lim > 0;
+  while (fused && S.hctrl->status == 0) {
+    if (fused_projcg_chunk(S, std::max(4 * chunk, 64), k == 0, xs, r, dc, Ad, rp, gp)) {
+      if (k == 0) { fused = false; break; }          // not eligible / launch refused before anything ran: unfused path
+      return -1;
+    }
+    k++;
+    if (read_ctrl(c, S)) return -1;
+  }
+  while (!fused && S.hctrl->status == 0) {
     for (int q = 0; q < chunk; q++, k++) {
       const int par = (int)(k & 1);
       int nph = hess_apply(S, Ad, dc, 1);
@@ -788,7 +809,10 @@ static int solve(lfpsqp_ctx *c, LargeState &S, const double *x0_host, double *x_
       else if (kind == 2) { if (retract_nr(c, S, &flag, &i1)) return S.cb_err ? LFPSQP_ERR_CALLBACK : LFPSQP_ERR_CUDA; }
       else { if (retract_pp(c, S, &flag, &i1, &i2)) return S.cb_err ? LFPSQP_ERR_CALLBACK : LFPSQP_ERR_CUDA; }
       S.retract_outer += i1; S.retract_pcg += i2; S.armijo_trials++;
-      if (flag > 0) { alpha *= prm.s; continue; }                                       // :57-60
+      // linesearch.jl:57-60 has no lower bound on alpha in this branch: when the retraction fails at EVERY alpha the
+      // reference spins forever once alpha has underflowed to 0.  Stop at the floor the other branch uses (:82-85):
+        // flag 98, LFPSQP_ST_NONFINITE.
+      if (flag > 0) { if (alpha < 1e-100) { flag = 98; break; } alpha *= prm.s; continue; }   // :57-60
       fam_f(S, xnew);
       vec(S, n, [=] __device__(int64_t i, double *acc) { double t = xnew[i] - x[i]; acc[0] += t * t; }, 1, 1);   // slot 1 only
       finalize(S, 3u, 0);
@@ -804,6 +828,7 @@ static int solve(lfpsqp_ctx *c, LargeState &S, const double *x0_host, double *x_
     }
     last_flag = flag;
     S.ms_linesearch += now_ms() - tl0;
+    if (flag == 98) { status |= LFPSQP_ST_NONFINITE; cond = LFPSQP_MAX_ITER; break; }
     cudaMemcpyAsync(x, xnew, nv * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);   // :424
     fval = newf;
     if (nobj < H) obj_hist[nobj] = fval;
@@ -895,7 +920,7 @@ extern "C" int lfpsqp_large_setup(lfpsqp_ctx *c, int family, int64_t n_global, i
   ok &= dalloc(S, &S.J, mm * S.ldj);
   ok &= dalloc(S, &S.G, mm * S.ldm); ok &= dalloc(S, &S.XT, mm * S.ldm); ok &= dalloc(S, &S.Linv, mm * S.ldm);
   ok &= dalloc(S, &S.Dblk, ((mm + 63) / 64) * 64 * 64); ok &= dalloc(S, &S.tmp64, mm * 64); ok &= dalloc(S, &S.thresh, 8);
-  S.gemm_ws_bytes = std::max<size_t>((size_t)16 * mm * 64 * 8, std::min<size_t>(mm * mm * 8 * 8, (size_t)256 << 20));
+  S.gemm_ws_bytes = std::max<size_t>((size_t)16 * mm * 64 * 8, std::min<size_t>(mm * mm * 8 * 16, (size_t)1 << 30));
   { char *ws = nullptr; ok &= dalloc(S, &ws, S.gemm_ws_bytes); S.gemm_ws = (double *)ws; }
   double **vecs[] = {&S.x, &S.xnew, &S.xtil, &S.g, &S.d, &S.nd, &S.w0, &S.w1, &S.w2, &S.w3, &S.w4, &S.hdiag};
   for (double **v : vecs) ok &= dalloc(S, v, 2 * nl + 2);   // [x-half | y-half] when bounds are set later
@@ -939,6 +964,10 @@ extern "C" int lfpsqp_large_setup(lfpsqp_ctx *c, int family, int64_t n_global, i
   cudaFuncSetAttribute(dgemm_nt_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgemm_smem_bytes<64>());
   cudaFuncSetAttribute(potf2_inv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 64 * 65 * sizeof(double)));
   CK(cudaStreamSynchronize(S.stream));
+  {
+    const char *env = getenv("LFPSQP_FUSED_PROJCG");   // "0" selects the multi-kernel projcg loop (A/B measurements, tests)
+    if (family == LFPSQP_FAM_DIAGQUAD && m > 0 && !(env && env[0] == '0')) fused_projcg_init(S, c->device);
+  }
   return LFPSQP_OK;
 }
 

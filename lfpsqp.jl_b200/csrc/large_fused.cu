@@ -1,0 +1,391 @@
+// large_fused.cu -- persistent, grid-synchronised projcg! (src/projcg.jl:71-112) for the large-n mode.
+//
+// The unfused path (large.cu::projcg) spends 8 dependent launches per CG iteration (11 with the cross-GPU all-reduces);
+// at C5 that is ~25 us of launch/drain gaps on top of 334 us of HBM time, and at 8 GPUs (41 us of HBM time per
+// iteration) the gaps dominate.  Here ONE cooperative kernel (one CTA per SM, 512 threads) runs a whole chunk of
+// iterations; the data dependencies between the phases of an iteration are grid barriers (cooperative groups), the CG
+// scalars are re-reduced redundantly by every CTA from per-CTA partials in a fixed order (bitwise identical on every
+// CTA => control flow stays grid-uniform), and projcg's exits (negative curvature, rg <= 0, ||g|| < tol, iteration
+// cap) are taken on the device exactly as in the unfused kernels.
+//
+// Phases of iteration k (B = grid barrier):
+//   P1  Ad = H d (diagonal Lagrangian Hessian: hd .* d), partial d.Ad            [owned columns]
+//   B   alpha = rg / d.Ad ; x += alpha d ; rp = r + alpha Ad                      [owned columns]       (projcg.jl:74-93)
+//   B   t = J rp                                                                  [owned rows, whole rows streamed]  (:96)
+//   B   y = L^-1 t                                                                [warp per row over the grid]
+//   B   u = L^-T y
+//   B   gp = rp - J' u ; partials rp.gp, gp.gp                                    [owned columns, all m rows streamed] (:97-99)
+//   B   beta = rp.gp / rg ; d = beta d - gp ; r = gp ; convergence tests          [owned columns]       (:98-111)
+// Algorithmic HBM bytes per iteration are those of the unfused path (16 m N + 8 m^2 + ~100 N); J is streamed with
+// 128-bit ld.global.nc.L1::no_allocate loads, vectors written inside the kernel are only read with coherent loads.
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "large_device.cuh"
+#include "large_state.h"
+
+namespace cg = cooperative_groups;
+using namespace lfpsqp;
+
+namespace {
+
+constexpr int FT = 512;      // threads per CTA
+constexpr int FR = 8;        // rows per sweep of the row phase
+constexpr int TR = 16;       // rows per sweep of the triangular phases
+constexpr int CU = 16;       // rows in flight per thread in the column phase
+
+struct FusedArgs {
+  int64_t n, ldj, ldm;       // local columns (even), leading dimensions
+  int m;
+  const double *J, *Linv, *XT, *hd;
+  double *xs, *dc, *r, *Ad, *rp, *gp, *tm, *ty, *tu;
+  double *part;              // 3 x gridDim partials: d.Ad | rp.gp | gp.gp
+  const double *lp_rg;       // first chunk: partials of r.r from cg_init (loop slot 3)
+  int np_rg, first, max_iters;
+  LargeCtrl *ctrl;
+  double *prof;              // nullptr, or 8 doubles: ns per phase summed over the chunk (debug)
+  // column-sharded mode (world > 1): the exported peer regions (push mailboxes, large_ctrl.h FZ_*), this rank, and the
+  // device-resident exchange counter (same sequence on every rank: the CG scalars are bitwise identical everywhere)
+  double *peer[PC_RANKS];
+  int rank, world;
+  unsigned long long *epoch;
+};
+
+// ---- in-kernel all-reduce over NVLink (push model).  Exchange e uses the mailboxes of parity e & 1; rank s may push
+// exchange e + 2 only after it has seen every flag e + 1, and a rank raises its flag e + 1 only behind a grid barrier
+// that follows all of its reads of exchange e: the double buffer is race-free.
+__device__ __forceinline__ void st_sys(double *p, double v) { asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ void fz_raise(const FusedArgs &a, unsigned long long e) {   // CTA 0, threads < world: my flag -> every rank
+  if ((int)threadIdx.x < a.world) {
+    unsigned long long *f = reinterpret_cast<unsigned long long *>(a.peer[threadIdx.x] + FZ_FLAG) + a.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(e) : "memory");
+  }
+}
+// every CTA: wait until all ranks have raised flag e (local polling); false on a 4 s timeout (a peer died)
+__device__ __forceinline__ bool fz_wait(const FusedArgs &a, unsigned long long e, int *timeout_flag) {
+  if ((int)threadIdx.x < a.world) {
+    const unsigned long long *f = reinterpret_cast<const unsigned long long *>(a.peer[a.rank] + FZ_FLAG) + threadIdx.x;
+    const long long t0 = clock64();
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+      if (v >= e) break;
+      if (clock64() - t0 > 8000000000LL) { *timeout_flag = 1; break; }
+    } while (true);
+  }
+  __syncthreads();
+  return *timeout_flag == 0;
+}
+// all-reduce of nv <= 4 scalars: `loc` is this rank's value (identical in every CTA); returns the rank-ordered sums in out[]
+__device__ __forceinline__ bool fz_allreduce_scal(const FusedArgs &a, unsigned long long e, const double *loc, int nv, double *out,
+                                                  int *timeout_flag) {
+  if (blockIdx.x == 0) {
+    if ((int)threadIdx.x < a.world) {
+      double *dst = a.peer[threadIdx.x] + FZ_SCAL + ((e & 1) * PC_RANKS + a.rank) * 4;
+      for (int k = 0; k < nv; k++) st_sys(dst + k, loc[k]);
+    }
+    fz_raise(a, e);      // same thread, same peer: the release store orders the data stores before the flag
+  }
+  if (!fz_wait(a, e, timeout_flag)) return false;
+  const double *src = a.peer[a.rank] + FZ_SCAL + (e & 1) * PC_RANKS * 4;
+  for (int k = 0; k < nv; k++) {
+    double s = 0.0;
+    for (int r = 0; r < a.world; r++) s += __ldcg(src + r * 4 + k);   // mailboxes are written by remote GPUs: read at L2
+    out[k] = s;
+  }
+  return true;
+}
+
+__device__ __forceinline__ double cta_sum_fixed(const double *p, int np, double *sh) {  // fixed-order sum, valid in every thread
+  double s = 0.0;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) s += p[i];
+  return block_sum(s, sh);
+}
+
+// NV independent CTA-wide sums with ONE barrier pair: warp butterflies (independent => latencies overlap), per-warp
+// partials through shared memory, thread q < NV ends up with the total of value q in v[0] (fixed order).
+template <int NV>
+__device__ __forceinline__ void cta_sum_multi(double (&v)[NV], double *shm /* (FT/32) * NV doubles */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NV; q++) v[q] = warp_sum(v[q]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; q++) shm[warp * NV + q] = v[q];
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0.0;
+    for (int w = 0; w < FT / 32; w++) s += shm[w * NV + threadIdx.x];
+    v[0] = s;
+  }
+}
+
+__global__ void __launch_bounds__(FT, 1) fused_projcg_kernel(FusedArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) double fsm[];            // [m] staged u | [FT] double2 scratch for the column phase
+  __shared__ double sh[33];
+  const int G = gridDim.x, c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n2 = a.n >> 1;
+  const int64_t P = (n2 + G - 1) / G;        // owned column pairs [p0, p1)
+  const int64_t p0 = min((int64_t)c * P, n2), p1 = min(p0 + P, n2);
+  const int m = a.m;
+  double *pA = a.part, *pB = a.part + G, *pC = a.part + 2 * G;
+  double *red_d = fsm + ((m + 1) & ~1);      // scratch after the staged u: FT double2
+  LargeCtrl *ctrl = a.ctrl;
+  double rg = a.first ? cta_sum_fixed(a.lp_rg, a.np_rg, sh) : ctrl->gg;
+  const double tol = ctrl->tol;
+  const int lim = ctrl->lim;
+  int iter = ctrl->iter, status = ctrl->status;
+  double dAd = 0.0, alpha = 0.0, beta = 0.0, rpgp = 0.0, gg = ctrl->gg, nr = ctrl->nr;
+  const bool multi = a.world > 1;
+  unsigned long long ep = multi ? *a.epoch : 0ULL;   // exchanges completed so far (every CTA counts the same sequence)
+  __shared__ int s_timeout;
+  if (tid == 0) s_timeout = 0;
+  __syncthreads();
+  grid.sync();                               // every CTA has read the control block before anyone may rewrite it
+  // optional phase profile (LFPSQP_FUSED_PROF=1): CTA 0 / thread 0 accumulates globaltimer deltas per phase
+  const bool prof = a.prof != nullptr && c == 0 && tid == 0;
+  unsigned long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+  auto tick = [&](int ph) {
+    if (prof) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); if (ph >= 0) tph[ph] += now - tlast; tlast = now; }
+  };
+  tick(-1);
+
+  for (int k = 0; k < a.max_iters && status == 0; k++) {
+    // ---- P1: Ad = hd .* d ; partial d.Ad
+    {
+      double s = 0.0;
+      for (int64_t p = p0 + tid; p < p1; p += FT) {
+        const double2 d2 = *reinterpret_cast<const double2 *>(a.dc + 2 * p);
+        const double2 h2 = *reinterpret_cast<const double2 *>(a.hd + 2 * p);
+        const double2 v = make_double2(h2.x * d2.x, h2.y * d2.y);
+        *reinterpret_cast<double2 *>(a.Ad + 2 * p) = v;
+        s += d2.x * v.x + d2.y * v.y;
+      }
+      s = block_sum(s, sh);
+      if (tid == 0) pA[c] = s;
+    }
+    grid.sync();
+    tick(0);
+    // ---- update1 (projcg.jl:74-93)
+    dAd = cta_sum_fixed(pA, G, sh);
+    if (multi) { double o; if (!fz_allreduce_scal(a, ++ep, &dAd, 1, &o, &s_timeout)) { status = 5; break; } dAd = o; }
+    iter++;
+    if (dAd <= 0.0) { status = 2; break; }
+    if (rg <= 0.0) { status = 3; break; }
+    alpha = rg / dAd;
+    for (int64_t p = p0 + tid; p < p1; p += FT) {
+      const double2 d2 = *reinterpret_cast<const double2 *>(a.dc + 2 * p);
+      const double2 r2 = *reinterpret_cast<const double2 *>(a.r + 2 * p);
+      const double2 A2 = *reinterpret_cast<const double2 *>(a.Ad + 2 * p);
+      double2 x2 = *reinterpret_cast<double2 *>(a.xs + 2 * p);
+      x2.x += alpha * d2.x; x2.y += alpha * d2.y;
+      *reinterpret_cast<double2 *>(a.xs + 2 * p) = x2;
+      *reinterpret_cast<double2 *>(a.rp + 2 * p) = make_double2(r2.x + alpha * A2.x, r2.y + alpha * A2.y);
+    }
+    grid.sync();
+    tick(1);
+    // ---- rows: t[i] = J[i] . rp for the rows i = c, c + G, ...  (FR rows per sweep, 2 x 128-bit loads per row in flight)
+    for (int i0 = c; i0 < m; i0 += G * FR) {
+      double acc[FR];
+#pragma unroll
+      for (int q = 0; q < FR; q++) acc[q] = 0.0;
+      for (int64_t j = tid; j < n2; j += FT * 2) {
+        const int64_t j1 = j + FT;
+        const bool ok1 = j1 < n2;
+        const double2 v0 = *reinterpret_cast<const double2 *>(a.rp + 2 * j);
+        const double2 v1 = ok1 ? *reinterpret_cast<const double2 *>(a.rp + 2 * j1) : make_double2(0.0, 0.0);
+        double2 q0[FR], q1[FR];
+#pragma unroll
+        for (int q = 0; q < FR; q++) {
+          const int i = i0 + q * G;
+          if (i < m) {
+            const double *row = a.J + (int64_t)i * a.ldj;
+            q0[q] = ld_stream2(row + 2 * j);
+            q1[q] = ok1 ? ld_stream2(row + 2 * j1) : make_double2(0.0, 0.0);
+          } else { q0[q] = make_double2(0.0, 0.0); q1[q] = make_double2(0.0, 0.0); }
+        }
+#pragma unroll
+        for (int q = 0; q < FR; q++) acc[q] += q0[q].x * v0.x + q0[q].y * v0.y + q1[q].x * v1.x + q1[q].y * v1.y;
+      }
+      cta_sum_multi<FR>(acc, red_d);
+      if (tid < FR && i0 + tid * G < m) {
+        const int i = i0 + tid * G;
+        if (!multi) a.tm[i] = acc[0];
+        else {  // push this rank's partial t_i into every rank's mailbox [parity][my rank]
+          const unsigned long long e = ep + 1;
+          for (int r = 0; r < a.world; r++) st_sys(a.peer[r] + FZ_VEC + ((e & 1) * PC_RANKS + a.rank) * (size_t)PC_MAX + i, acc[0]);
+        }
+      }
+    }
+    if (multi) __threadfence_system();
+    grid.sync();
+    if (multi) {   // every CTA's pushes are ordered before the barrier: raise the flag, wait for everybody, then t = rank-ordered sum
+      ++ep;
+      if (c == 0) fz_raise(a, ep);
+      if (!fz_wait(a, ep, &s_timeout)) { status = 5; break; }
+    }
+    tick(2);
+    // ---- y = L^-1 t (lower), then u = L^-T y (XT upper).  The CTA owns the rows c, c + G, ... and works on TR of them at
+    // once: every thread takes the same k-slices of all TR rows (TR x 128-bit loads in flight), one reduction per sweep.
+    for (int pass = 0; pass < 2; pass++) {
+      const double *T = pass ? a.XT : a.Linv;
+      const double *in = pass ? a.ty : a.tm;
+      double *out = pass ? a.tu : a.ty;
+      const int m2 = (m + 1) >> 1;
+      for (int i0 = c; i0 < m; i0 += G * TR) {
+        double acc[TR];
+#pragma unroll
+        for (int q = 0; q < TR; q++) acc[q] = 0.0;
+        for (int k2 = tid; k2 < m2; k2 += FT) {
+          const int k = 2 * k2;
+          double v0, v1;
+          if (multi && pass == 0) {
+            const double *mb = a.peer[a.rank] + FZ_VEC + (ep & 1) * (size_t)PC_RANKS * PC_MAX;
+            v0 = 0.0; v1 = 0.0;
+            for (int r = 0; r < a.world; r++) { v0 += __ldcg(mb + (size_t)r * PC_MAX + k); if (k + 1 < m) v1 += __ldcg(mb + (size_t)r * PC_MAX + k + 1); }
+          } else { v0 = in[k]; v1 = (k + 1 < m) ? in[k + 1] : 0.0; }
+#pragma unroll
+          for (int q = 0; q < TR; q++) {
+            const int row = i0 + q * G;
+            if (row >= m) continue;
+            // lower: k <= row ; upper: k >= row (the other triangle of the row-major factor holds zeros or garbage: mask)
+            const bool ok0 = pass ? (k >= row) : (k <= row), ok1 = pass ? (k + 1 >= row && k + 1 < m) : (k + 1 <= row);
+            if (!(ok0 || ok1)) continue;
+            const double2 w = *reinterpret_cast<const double2 *>(T + (int64_t)row * a.ldm + k);
+            acc[q] += (ok0 ? w.x * v0 : 0.0) + (ok1 ? w.y * v1 : 0.0);
+          }
+        }
+        cta_sum_multi<TR>(acc, red_d);
+        if (tid < TR && i0 + tid * G < m) out[i0 + tid * G] = acc[0];
+      }
+      grid.sync();
+      tick(3 + pass);
+    }
+    // ---- cols: gp = rp - J' u on the owned columns ; partials rp.gp, gp.gp
+    {
+      for (int i = tid; i < m; i += FT) fsm[i] = a.tu[i];
+      __syncthreads();
+      double2 *red = reinterpret_cast<double2 *>(red_d);
+      double sb = 0.0, sc = 0.0;
+      for (int64_t pc = p0; pc < p1; pc += FT) {
+        const int PW = (int)min((int64_t)FT, p1 - pc);
+        const int RG = FT / PW;                       // row groups sharing one column pair
+        const int g = tid / PW, pl = tid - g * PW;
+        double a0 = 0.0, a1 = 0.0;
+        if (g < RG) {
+          const double *base = a.J + 2 * (pc + pl);
+          int i = g;
+          for (; i + (CU - 1) * RG < m; i += CU * RG) {
+            double2 q[CU];
+#pragma unroll
+            for (int e = 0; e < CU; e++) q[e] = ld_stream2(base + (int64_t)(i + e * RG) * a.ldj);
+#pragma unroll
+            for (int e = 0; e < CU; e++) { const double w = fsm[i + e * RG]; a0 += q[e].x * w; a1 += q[e].y * w; }
+          }
+          for (; i < m; i += RG) { const double2 q = ld_stream2(base + (int64_t)i * a.ldj); const double w = fsm[i]; a0 += q.x * w; a1 += q.y * w; }
+        }
+        __syncthreads();
+        red[tid] = make_double2(a0, a1);
+        __syncthreads();
+        if (g == 0) {
+          double s0 = 0.0, s1 = 0.0;
+          for (int e = 0; e < RG; e++) { const double2 v = red[e * PW + pl]; s0 += v.x; s1 += v.y; }
+          const int64_t p = pc + pl;
+          const double2 rp2 = *reinterpret_cast<const double2 *>(a.rp + 2 * p);
+          const double2 g2 = make_double2(rp2.x - s0, rp2.y - s1);
+          *reinterpret_cast<double2 *>(a.gp + 2 * p) = g2;
+          sb += rp2.x * g2.x + rp2.y * g2.y; sc += g2.x * g2.x + g2.y * g2.y;
+        }
+      }
+      sb = block_sum(sb, sh); sc = block_sum(sc, sh);
+      if (tid == 0) { pB[c] = sb; pC[c] = sc; }
+    }
+    grid.sync();
+    tick(5);
+    // ---- update3 (projcg.jl:98-111)
+    rpgp = cta_sum_fixed(pB, G, sh);
+    gg = cta_sum_fixed(pC, G, sh);
+    if (multi) {
+      double loc[2] = {rpgp, gg}, o[2];
+      if (!fz_allreduce_scal(a, ++ep, loc, 2, o, &s_timeout)) { status = 5; break; }
+      rpgp = o[0]; gg = o[1];
+    }
+    beta = rpgp / rg;
+    for (int64_t p = p0 + tid; p < p1; p += FT) {
+      const double2 g2 = *reinterpret_cast<const double2 *>(a.gp + 2 * p);
+      double2 d2 = *reinterpret_cast<double2 *>(a.dc + 2 * p);
+      d2.x = beta * d2.x - g2.x; d2.y = beta * d2.y - g2.y;
+      *reinterpret_cast<double2 *>(a.dc + 2 * p) = d2;
+      *reinterpret_cast<double2 *>(a.r + 2 * p) = g2;
+    }
+    nr = sqrt(gg);
+    rg = gg;                                    // r == g after every projection (:100-101)
+    if (nr < tol) status = 1; else if (iter >= lim) status = 4;
+    tick(6);
+    // no barrier: the next P1 touches only this CTA's own columns; pA is next written after every CTA has passed the
+    // barrier that follows its last read of pB/pC
+  }
+  if (prof) for (int q = 0; q < 8; q++) a.prof[q] = (double)tph[q];
+  if (c == 0 && tid == 0) {
+    if (multi) *a.epoch = ep;
+    if (status == 5) ctrl->rankflag = 99;
+    ctrl->iter = iter; ctrl->status = status; ctrl->dAd = dAd; ctrl->alpha = alpha; ctrl->beta = beta;
+    ctrl->rpgp = rpgp; ctrl->gg = gg; ctrl->rg = rg; ctrl->nr = nr;
+  }
+}
+
+}  // namespace
+
+// Returns 0 when the chunk was enqueued, 1 when this configuration is not eligible (the caller uses the unfused path).
+int fused_projcg_chunk(LargeState &S, int iters, int first, double *xs, double *r, double *dc, double *Ad, double *rp, double *gp) {
+  if (S.ineq || S.family != LFPSQP_FAM_DIAGQUAD || (S.n_loc & 1) || S.m < 1 || !S.fused_ok) return 1;
+  if (S.world > 1 && !(S.comm && S.comm->peer_ready && S.m <= PC_MAX && S.world <= PC_RANKS)) return 1;
+  FusedArgs a;
+  for (int r = 0; r < PC_RANKS; r++) a.peer[r] = (S.world > 1) ? S.comm->peer_map[r] : nullptr;
+  a.rank = S.rank; a.world = S.world; a.epoch = (S.world > 1) ? reinterpret_cast<unsigned long long *>(S.comm->peer_local + FZ_FLAG + PC_RANKS) : nullptr;   // lives with the region
+  a.n = S.n_loc; a.ldj = S.ldj; a.ldm = S.ldm; a.m = S.m;
+  a.J = S.J; a.Linv = S.Linv; a.XT = S.XT; a.hd = S.hdiag;
+  a.xs = xs; a.dc = dc; a.r = r; a.Ad = Ad; a.rp = rp; a.gp = gp; a.tm = S.tm; a.ty = S.ty; a.tu = S.tu;
+  a.part = S.fused_part; a.lp_rg = S.lp + 3 * (size_t)MAXP; a.np_rg = S.np_loop; a.first = first; a.max_iters = iters;
+  a.ctrl = S.ctrl;
+  static const bool want_prof = getenv("LFPSQP_FUSED_PROF") != nullptr;
+  a.prof = want_prof ? S.fused_part + 3 * (size_t)S.fused_grid : nullptr;
+  const size_t smem = ((size_t)((S.m + 1) & ~1) + 2 * FT) * sizeof(double);
+  void *args[] = {&a};
+  cudaError_t e = cudaLaunchCooperativeKernel((void *)fused_projcg_kernel, dim3(S.fused_grid), dim3(FT), args, smem, S.stream);
+  if (e != cudaSuccess) { cudaGetLastError(); S.fused_ok = false; return 1; }
+  S.launches++;
+  if (want_prof) {
+    double h[8];
+    cudaMemcpyAsync(h, a.prof, sizeof(h), cudaMemcpyDeviceToHost, S.stream);
+    cudaStreamSynchronize(S.stream);
+    fprintf(stderr, "[fused projcg] %d iterations max; us per phase over the chunk: hess %.1f | update1 %.1f | rows %.1f | tri1 %.1f | tri2 %.1f | cols %.1f | update3 %.1f\n",
+            iters, h[0] / 1e3, h[1] / 1e3, h[2] / 1e3, h[3] / 1e3, h[4] / 1e3, h[5] / 1e3, h[6] / 1e3);
+  }
+  return 0;
+}
+
+// one-time eligibility probe: cooperative launch support, co-residency of one CTA per SM with the dynamic shared memory
+void fused_projcg_init(LargeState &S, int device) {
+  S.fused_ok = false;
+  int coop = 0;
+  if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) != cudaSuccess || !coop) { cudaGetLastError(); return; }
+  const size_t smem = ((size_t)((S.m + 1) & ~1) + 2 * FT) * sizeof(double);
+  if (smem > 200 * 1024) return;
+  if (cudaFuncSetAttribute(fused_projcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return; }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_projcg_kernel, FT, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return; }
+  S.fused_grid = S.sm_count;
+  void *p = nullptr;
+  if (cudaMalloc(&p, (3 * (size_t)S.fused_grid + 16) * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return; }
+  cudaMemset(p, 0, (3 * (size_t)S.fused_grid + 16) * sizeof(double));
+  S.owned.push_back(p); S.fused_part = (double *)p;
+  S.fused_ok = true;
+}

@@ -21,6 +21,10 @@ struct LargeState {
   lfpsqp_host_callbacks cb = {};
   double *hx = nullptr, *hv = nullptr, *hw = nullptr, *hlam = nullptr, *hc = nullptr, *hJ = nullptr, *Jstage = nullptr;
   int cb_err = 0;
+  // persistent fused projcg (large_fused.cu)
+  bool fused_ok = false;
+  int fused_grid = 0;
+  double *fused_part = nullptr;
   int m = 0, sm_count = 148, world = 1, rank = 0;
   cudaStream_t stream = nullptr;
   lfpsqp_params prm;
@@ -54,6 +58,10 @@ struct LargeState {
     newton_accepted = factorizations = f_evals = 0;
   }
 };
+
+// large_fused.cu: one cooperative kernel per chunk of projcg iterations (returns 1 when not eligible -> unfused path)
+int fused_projcg_chunk(LargeState &S, int iters, int first, double *xs, double *r, double *dc, double *Ad, double *rp, double *gp);
+void fused_projcg_init(LargeState &S, int device);
 
 // comm.cu
 void comm_allreduce(LargeState &S, double *buf, size_t count);                  // in-place sum over ranks

@@ -4,6 +4,7 @@
 # NOTE: Julia is not installed in the build image, so this file has never been executed; the identical call sequence
 # is exercised through the ctypes mirror `lfpsqp.jl_b200/api.py`.  No CUDA.jl, no array dispatch: plain pointers.
 module LFPSQPB200
+import Random
 
 export optimize, optimize_batched, LFPSQPParams, TerminationInfo, DeviceFamily, rosenbrock, readme_equality,
        readme_inequality, thomson, diagquad
@@ -76,5 +77,66 @@ function optimize(fam::DeviceFamily, x0::Vector{Float64}, xl, xu, param::LFPSQPP
     x[:, 1], obj[1:len[1], 1], λ[:, 1], TerminationInfo(TerminationCondition(t.condition), t.f_diff, t.step_diff, t.kkt_diff, t.iter)
 end
 optimize(fam::DeviceFamily, x0::Vector{Float64}, param::LFPSQPParams=LFPSQPParams()) = optimize(fam, x0, nothing, nothing, param)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Generic problems: the explicit-derivative core optimize(f, grad!, c!, jac!, hess_lag_vec!, x0, xl, xu, m, param)
+# (src/optimize.jl:119-443) over lfpsqp_solve_host.  The callbacks are the reference's own closures (AD-generated by
+# src/autodiff_generators.jl or hand-written); they run on the host, the linear algebra on the device.
+struct HostCallbacks              # lfpsqp_host_callbacks (include/lfpsqp_b200.h)
+    user::Ptr{Cvoid}; f::Ptr{Cvoid}; grad::Ptr{Cvoid}; c::Ptr{Cvoid}; jac::Ptr{Cvoid}; hess::Ptr{Cvoid}
+    callback::Ptr{Cvoid}; randn::Ptr{Cvoid}
+end
+mutable struct HostProblem
+    f; grad!; c!; jac!; hess_lag_vec!; callback; err::Any
+end
+_prob(u) = unsafe_pointer_to_objref(u)::HostProblem
+_w(p, dims...) = unsafe_wrap(Array, p, dims)
+# exceptions must not unwind through C: store them, return 1 (=> LFPSQP_ERR_CALLBACK), rethrow after the ccall
+macro guarded(u, ex)
+    quote
+        try
+            $(esc(ex)); Cint(0)
+        catch e
+            _prob($(esc(u))).err = e; Cint(1)
+        end
+    end
+end
+_f(u, x, n, out)::Cint = @guarded u unsafe_store!(out, _prob(u).f(_w(x, n)))
+_grad(u, g, x, n)::Cint = @guarded u _prob(u).grad!(_w(g, n), _w(x, n))
+_c(u, cv, x, n, m)::Cint = @guarded u _prob(u).c!(_w(cv, m), _w(x, n))
+_jac(u, Jc, cv, x, n, m)::Cint = @guarded u _prob(u).jac!(_w(Jc, m, n), _w(cv, m), _w(x, n))     # Jc m x n column-major (optimize.jl:189)
+_hess(u, dest, src, x, lam, n, m)::Cint = @guarded u _prob(u).hess_lag_vec!(_w(dest, n), _w(src, n), _w(x, n), _w(lam, m))
+_cb(u, i, x, na)::Cint = @guarded u _prob(u).callback(i, _w(x, na))                               # optimize.jl:432-434
+_randn(u, buf, na)::Cint = @guarded u Random.randn!(_w(buf, na))                                  # optimize.jl:264-273
+
+function optimize(f, grad!, c!, jac!, hess_lag_vec!, x0::Vector{Float64}, xl, xu, m::Int64,
+                  param::LFPSQPParams=LFPSQPParams(); callback=nothing)
+    n = length(x0)
+    if !isnothing(xl) && !isnothing(xu) && !(length(xl) == length(xu) == n)
+        error("xl, xu, and x0 must all be the same length")                                       # optimize.jl:144-148
+    end
+    prob = HostProblem(f, grad!, c!, jac!, hess_lag_vec!, callback, nothing)
+    P = Ptr{Cvoid}; D = Ptr{Float64}
+    cb = HostCallbacks(pointer_from_objref(prob),
+        @cfunction(_f, Cint, (P, D, Int64, D)), @cfunction(_grad, Cint, (P, D, D, Int64)),
+        m > 0 ? @cfunction(_c, Cint, (P, D, D, Int64, Int64)) : C_NULL,
+        m > 0 ? @cfunction(_jac, Cint, (P, D, D, D, Int64, Int64)) : C_NULL,
+        @cfunction(_hess, Cint, (P, D, D, D, D, Int64, Int64)),
+        isnothing(callback) ? C_NULL : @cfunction(_cb, Cint, (P, Int64, D, Int64)),
+        param.β > 0 ? @cfunction(_randn, Cint, (P, D, Int64)) : C_NULL)
+    H = param.maxiter + 1
+    x = Vector{Float64}(undef, n); obj = Vector{Float64}(undef, H); len = Ref{Int64}(0)
+    λ = Vector{Float64}(undef, max(m, 1)); term = Ref{CTerm}()
+    pl = isnothing(xl) ? D(C_NULL) : pointer(xl); pu = isnothing(xu) ? D(C_NULL) : pointer(xu)
+    rc = GC.@preserve prob x0 xl xu x obj λ ccall((:lfpsqp_solve_host, lib), Cint,
+            (P, Ref{HostCallbacks}, Int64, Int64, D, D, D, Ref{LFPSQPParams}, D, D, Int64, Ref{Int64}, D, Ref{CTerm}, P),
+            context(), cb, n, m, x0, pl, pu, param, x, obj, H, len, λ, term, C_NULL)
+    isnothing(prob.err) || throw(prob.err)
+    check(rc)
+    t = term[]
+    t.iter == param.maxiter && @warn "Maximum # of outer iterations reached"                      # optimize.jl:438-440
+    x, obj[1:len[]], λ[1:m], TerminationInfo(TerminationCondition(t.condition), t.f_diff, t.step_diff, t.kkt_diff, t.iter)
+end
 
 end # module

@@ -72,18 +72,21 @@ def test_edge_cases(L, oracle):
                                   fam_params=f1.params, fam_stride=3, nthreads=1)
     assert np.array_equal(gpu[4]["condition"], orc[4]["condition"])
     assert np.allclose(gpu[0], orc[0], atol=1e-7) and np.allclose(gpu[0].ravel(), [1.0, -1.0, 0.2], atol=1e-3)
-    # large-n mode argument errors mirror optimize.jl:160-162 / unsupported finite bounds are refused, not ignored
+    # large-n mode through the one-call entry point: finite bounds run the 2n embedding; xl > xu mirrors optimize.jl:160-162
     import ctypes as C
     from lfpsqp.jl_b200 import _lib
     ctx = L.default_context(0)
     Q, A, b, xt, w, x0 = L.make_diagquad(64, 4, seed=1)
     blob = np.concatenate([Q.ravel(), A.ravel(), b, xt, w])
     prm = L.LFPSQPParams().to_c()
-    out = np.zeros(64); obj = np.zeros(8); ol = np.zeros(1, dtype=np.int64); lam = np.zeros(4); term = np.zeros(1, dtype=_lib.TERM_DTYPE)
-    zeros, ones = np.zeros(64), np.ones(64)     # keep the host buffers alive across the calls
-    rc = ctx.lib.lfpsqp_solve_large(ctx.h, L.families.DIAGQUAD, 64, 4, _lib.ptr(blob), _lib.ptr(x0), _lib.ptr(zeros), _lib.ptr(ones),
-                                    C.cast(C.pointer(prm), C.c_void_p), _lib.ptr(out), _lib.ptr(obj), 8, _lib.ptr(ol), _lib.ptr(lam), _lib.ptr(term), None)
-    assert rc == -4 and b"bounds" in ctx.lib.lfpsqp_last_error(ctx.h)
-    rc = ctx.lib.lfpsqp_solve_large(ctx.h, L.families.DIAGQUAD, 64, 4, _lib.ptr(blob), _lib.ptr(x0), _lib.ptr(ones), _lib.ptr(zeros),
-                                    C.cast(C.pointer(prm), C.c_void_p), _lib.ptr(out), _lib.ptr(obj), 8, _lib.ptr(ol), _lib.ptr(lam), _lib.ptr(term), None)
+    out = np.zeros(64); obj = np.zeros(64); ol = np.zeros(1, dtype=np.int64); lam = np.zeros(4); term = np.zeros(1, dtype=_lib.TERM_DTYPE)
+    lo, hi = x0 - 0.5, x0 + 0.5     # keep the host buffers alive across the calls
+    rc = ctx.lib.lfpsqp_solve_large(ctx.h, L.families.DIAGQUAD, 64, 4, _lib.ptr(blob), _lib.ptr(x0), _lib.ptr(lo), _lib.ptr(hi),
+                                    C.cast(C.pointer(prm), C.c_void_p), _lib.ptr(out), _lib.ptr(obj), 64, _lib.ptr(ol), _lib.ptr(lam), _lib.ptr(term), None)
+    assert rc == 0 and term[0]["status"] == 0 and np.all(out >= lo - 2e-5) and np.all(out <= hi + 2e-5)
+    ox = oracle.optimize("diagquad", 64, 4, 0, x0, xl=lo, xu=hi, fam_params=blob)
+    assert term[0]["condition"] == ox[3]["condition"] and abs(int(term[0]["iter"]) - ox[3]["iter"]) <= 1
+    assert np.linalg.norm(out - ox[0]) <= 1e-6 * np.linalg.norm(ox[0])
+    rc = ctx.lib.lfpsqp_solve_large(ctx.h, L.families.DIAGQUAD, 64, 4, _lib.ptr(blob), _lib.ptr(x0), _lib.ptr(hi), _lib.ptr(lo),
+                                    C.cast(C.pointer(prm), C.c_void_p), _lib.ptr(out), _lib.ptr(obj), 64, _lib.ptr(ol), _lib.ptr(lam), _lib.ptr(term), None)
     assert rc == -2
