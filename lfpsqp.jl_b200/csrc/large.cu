@@ -322,6 +322,9 @@ static int factorize(lfpsqp_ctx *c, LargeState &S) {
   }
   dim3 tg((m + 31) / 32, (m + 31) / 32);
   transpose_kernel<<<tg, 256, 0, S.stream>>>(S.XT, ldm, S.Linv, ldm, m, m);
+  if (S.fused_ok && S.Ginv) {   // G^-1 = L^-T L^-1 = XT XT' for the fused projcg kernel (large_fused.cu): one more DMMA GEMM, m^3 flops
+    gemm_nt(S, m, m, m, S.XT, ldm, S.XT, ldm, S.Ginv, ldm, GEMM_ASSIGN, 0);
+  }
   S.launches += 3;
   S.factorizations++;
   (void)c;

@@ -54,9 +54,18 @@ __device__ __forceinline__ double reduce_partials_max(const double *part, int np
   return block_max(s, sh);
 }
 
-__device__ __forceinline__ double2 ld_stream2(const double *p) {  // streaming 128-bit load, do not keep in L1
+// Streaming 128-bit load for data that is read once per pass (J, Q, A: GiB-sized): not kept in L1 and marked
+// evict-first in L2, so that the m x m factors and the n-vectors, which ARE re-read every iteration, stay resident in
+// the 126 MB L2 while the stream passes through.
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+  unsigned long long pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ double2 ld_stream2(const double *p) {
   double2 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  const unsigned long long pol = l2_evict_first_policy();
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;\n" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
   return v;
 }
 

@@ -12,13 +12,11 @@
 //   P1  Ad = H d (diagonal Lagrangian Hessian: hd .* d), partial d.Ad            [owned columns]
 //   B   alpha = rg / d.Ad ; x += alpha d ; rp = r + alpha Ad                      [owned columns]       (projcg.jl:74-93)
 //   B   t = J rp                                                                  [owned rows, whole rows streamed]  (:96)
-//   B   y = L^-1 t                                                                [warp per row over the grid]
-//   B   u = L^-T y
+//   B   u = G^-1 t  (explicit G^-1 = L^-T L^-1, one m x m pass)                    [owned rows]
 //   B   gp = rp - J' u ; partials rp.gp, gp.gp                                    [owned columns, all m rows streamed] (:97-99)
 //   B   beta = rp.gp / rg ; d = beta d - gp ; r = gp ; convergence tests          [owned columns]       (:98-111)
 // Algorithmic HBM bytes per iteration are those of the unfused path (16 m N + 8 m^2 + ~100 N); J is streamed with
 // 128-bit ld.global.nc.L1::no_allocate loads, vectors written inside the kernel are only read with coherent loads.
-#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -28,7 +26,6 @@
 #include "large_device.cuh"
 #include "large_state.h"
 
-namespace cg = cooperative_groups;
 using namespace lfpsqp;
 
 namespace {
@@ -36,13 +33,14 @@ namespace {
 constexpr int FT = 512;      // threads per CTA
 constexpr int FR = 8;        // rows per sweep of the row phase
 constexpr int TR = 16;       // rows per sweep of the triangular phases
-constexpr int CU = 16;       // rows in flight per thread in the column phase
+constexpr int CU = 16;       // 128-bit loads in flight per thread in the streaming phases
+constexpr int RCH = 2048;    // column pairs per shared-memory chunk of rp in the row phase (2 buffers x 32 KB)
 
 struct FusedArgs {
   int64_t n, ldj, ldm;       // local columns (even), leading dimensions
   int m;
-  const double *J, *Linv, *XT, *hd;
-  double *xs, *dc, *r, *Ad, *rp, *gp, *tm, *ty, *tu;
+  const double *J, *Ginv, *hd;
+  double *xs, *dc, *r, *Ad, *rp, *gp, *tm, *tu;
   double *part;              // 3 x gridDim partials: d.Ad | rp.gp | gp.gp
   const double *lp_rg;       // first chunk: partials of r.r from cg_init (loop slot 3)
   int np_rg, first, max_iters;
@@ -53,6 +51,8 @@ struct FusedArgs {
   double *peer[PC_RANKS];
   int rank, world;
   unsigned long long *epoch;
+  unsigned *bar;             // grid-barrier arrival counter
+  int rows_mode;
 };
 
 // ---- in-kernel all-reduce over NVLink (push model).  Exchange e uses the mailboxes of parity e & 1; rank s may push
@@ -126,8 +126,26 @@ __device__ __forceinline__ void cta_sum_multi(double (&v)[NV], double *shm /* (F
   }
 }
 
+// Grid barrier of the cooperative launch: one monotone arrival counter (zeroed by the host before every launch);
+// thread 0 of each CTA arrives with a release-add at gpu scope and spins with acquire loads until everybody of this
+// generation has arrived.  Co-residency of all CTAs is guaranteed by cudaLaunchCooperativeKernel.
+struct GridBar {
+  unsigned *ctr; unsigned gen, nblk;
+  __device__ __forceinline__ void sync() {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      gen++;
+      const unsigned target = gen * nblk;
+      asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
+      unsigned v;
+      do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory"); } while (v < target);
+    }
+    __syncthreads();
+  }
+};
+
 __global__ void __launch_bounds__(FT, 1) fused_projcg_kernel(FusedArgs a) {
-  cg::grid_group grid = cg::this_grid();
+  GridBar grid{a.bar, 0u, gridDim.x};
   extern __shared__ __align__(16) double fsm[];            // [m] staged u | [FT] double2 scratch for the column phase
   __shared__ double sh[33];
   const int G = gridDim.x, c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -137,6 +155,7 @@ __global__ void __launch_bounds__(FT, 1) fused_projcg_kernel(FusedArgs a) {
   const int m = a.m;
   double *pA = a.part, *pB = a.part + G, *pC = a.part + 2 * G;
   double *red_d = fsm + ((m + 1) & ~1);      // scratch after the staged u: FT double2
+  double2 *vch = reinterpret_cast<double2 *>(red_d + 2 * FT);   // 2 x RCH double2: rp chunks of the row phase
   LargeCtrl *ctrl = a.ctrl;
   double rg = a.first ? cta_sum_fixed(a.lp_rg, a.np_rg, sh) : ctrl->gg;
   const double tol = ctrl->tol;
@@ -191,36 +210,52 @@ __global__ void __launch_bounds__(FT, 1) fused_projcg_kernel(FusedArgs a) {
     }
     grid.sync();
     tick(1);
-    // ---- rows: t[i] = J[i] . rp for the rows i = c, c + G, ...  (FR rows per sweep, 2 x 128-bit loads per row in flight)
-    for (int i0 = c; i0 < m; i0 += G * FR) {
-      double acc[FR];
+    // ---- rows: t[i] = J[i] . rp.  One WARP per row (rows i = c + w G of warp w: every row of the CTA is streamed
+    // concurrently, so the bytes in flight stay constant over the whole phase and all CTAs finish together); rp goes
+    // through double-buffered shared-memory chunks (one L2 read per CTA instead of one per row); CU x 128-bit loads
+    // in flight per lane.
+    {
+      const double2 *rp2 = reinterpret_cast<const double2 *>(a.rp);
+      for (int pass0 = 0; c + (int64_t)pass0 * (FT / 32) * G < m; pass0++) {
+        // rows_mode 0: rows c + w G (neighbouring CTAs stream neighbouring rows); 1: a contiguous block of rows per CTA
+        const int rpc = (m + G - 1) / G;
+        const int wq = pass0 * (FT / 32) + warp;
+        const int i = a.rows_mode ? (wq < rpc ? c * rpc + wq : m) : c + wq * G;
+        const bool act = i < m;
+        const double *row = a.J + (int64_t)(act ? i : 0) * a.ldj;
+        const int nch = (int)((n2 + RCH - 1) / RCH);
+        double acc = 0.0;
+        __syncthreads();
+        for (int p = tid; p < (int)min((int64_t)RCH, n2); p += FT) vch[p] = rp2[p];
+        __syncthreads();
+        for (int ch = 0; ch < nch; ch++) {
+          const double2 *cur = vch + (ch & 1) * RCH;
+          double2 *nxt = vch + ((ch + 1) & 1) * RCH;
+          const int64_t base = (int64_t)ch * RCH;
+          const int len = (int)min((int64_t)RCH, n2 - base);
+          if (ch + 1 < nch) {
+            const int nlen = (int)min((int64_t)RCH, n2 - base - RCH);
+            for (int p = tid; p < nlen; p += FT) nxt[p] = rp2[base + RCH + p];
+          }
+          if (act) {
+            const double *rb = row + 2 * base;
+            for (int p = lane; p < len; p += 32 * CU) {
+              double2 q[CU];
 #pragma unroll
-      for (int q = 0; q < FR; q++) acc[q] = 0.0;
-      for (int64_t j = tid; j < n2; j += FT * 2) {
-        const int64_t j1 = j + FT;
-        const bool ok1 = j1 < n2;
-        const double2 v0 = *reinterpret_cast<const double2 *>(a.rp + 2 * j);
-        const double2 v1 = ok1 ? *reinterpret_cast<const double2 *>(a.rp + 2 * j1) : make_double2(0.0, 0.0);
-        double2 q0[FR], q1[FR];
+              for (int e = 0; e < CU; e++) { const int pp = p + e * 32; q[e] = (pp < len) ? ld_stream2(rb + 2 * pp) : make_double2(0.0, 0.0); }
 #pragma unroll
-        for (int q = 0; q < FR; q++) {
-          const int i = i0 + q * G;
-          if (i < m) {
-            const double *row = a.J + (int64_t)i * a.ldj;
-            q0[q] = ld_stream2(row + 2 * j);
-            q1[q] = ok1 ? ld_stream2(row + 2 * j1) : make_double2(0.0, 0.0);
-          } else { q0[q] = make_double2(0.0, 0.0); q1[q] = make_double2(0.0, 0.0); }
+              for (int e = 0; e < CU; e++) { const int pp = p + e * 32; if (pp < len) { const double2 v = cur[pp]; acc += q[e].x * v.x + q[e].y * v.y; } }
+            }
+          }
+          __syncthreads();
         }
-#pragma unroll
-        for (int q = 0; q < FR; q++) acc[q] += q0[q].x * v0.x + q0[q].y * v0.y + q1[q].x * v1.x + q1[q].y * v1.y;
-      }
-      cta_sum_multi<FR>(acc, red_d);
-      if (tid < FR && i0 + tid * G < m) {
-        const int i = i0 + tid * G;
-        if (!multi) a.tm[i] = acc[0];
-        else {  // push this rank's partial t_i into every rank's mailbox [parity][my rank]
-          const unsigned long long e = ep + 1;
-          for (int r = 0; r < a.world; r++) st_sys(a.peer[r] + FZ_VEC + ((e & 1) * PC_RANKS + a.rank) * (size_t)PC_MAX + i, acc[0]);
+        acc = warp_sum(acc);
+        if (lane == 0 && act) {
+          if (!multi) a.tm[i] = acc;
+          else {  // push this rank's partial t_i into every rank's mailbox [parity][my rank]
+            const unsigned long long e = ep + 1;
+            for (int r = 0; r < a.world; r++) st_sys(a.peer[r] + FZ_VEC + ((e & 1) * PC_RANKS + a.rank) * (size_t)PC_MAX + i, acc);
+          }
         }
       }
     }
@@ -232,12 +267,11 @@ __global__ void __launch_bounds__(FT, 1) fused_projcg_kernel(FusedArgs a) {
       if (!fz_wait(a, ep, &s_timeout)) { status = 5; break; }
     }
     tick(2);
-    // ---- y = L^-1 t (lower), then u = L^-T y (XT upper).  The CTA owns the rows c, c + G, ... and works on TR of them at
-    // once: every thread takes the same k-slices of all TR rows (TR x 128-bit loads in flight), one reduction per sweep.
-    for (int pass = 0; pass < 2; pass++) {
-      const double *T = pass ? a.XT : a.Linv;
-      const double *in = pass ? a.ty : a.tm;
-      double *out = pass ? a.tu : a.ty;
+    // ---- u = G^-1 t with the explicit symmetric inverse G^-1 = L^-T L^-1 (formed once per factorisation by a DMMA
+    // GEMM): ONE grid phase instead of two dependent triangular ones.  The CTA owns the rows c, c + G, ... and works
+    // on TR of them at once: every thread takes the same k-slices of all TR rows (TR x 128-bit loads in flight), one
+    // CTA-wide reduction per sweep.
+    {
       const int m2 = (m + 1) >> 1;
       for (int i0 = c; i0 < m; i0 += G * TR) {
         double acc[TR];
@@ -245,28 +279,26 @@ __global__ void __launch_bounds__(FT, 1) fused_projcg_kernel(FusedArgs a) {
         for (int q = 0; q < TR; q++) acc[q] = 0.0;
         for (int k2 = tid; k2 < m2; k2 += FT) {
           const int k = 2 * k2;
+          const bool has1 = k + 1 < m;
           double v0, v1;
-          if (multi && pass == 0) {
+          if (multi) {   // t = rank-ordered sum of the mailboxes (written by remote GPUs: read at L2)
             const double *mb = a.peer[a.rank] + FZ_VEC + (ep & 1) * (size_t)PC_RANKS * PC_MAX;
             v0 = 0.0; v1 = 0.0;
-            for (int r = 0; r < a.world; r++) { v0 += __ldcg(mb + (size_t)r * PC_MAX + k); if (k + 1 < m) v1 += __ldcg(mb + (size_t)r * PC_MAX + k + 1); }
-          } else { v0 = in[k]; v1 = (k + 1 < m) ? in[k + 1] : 0.0; }
+            for (int r = 0; r < a.world; r++) { v0 += __ldcg(mb + (size_t)r * PC_MAX + k); if (has1) v1 += __ldcg(mb + (size_t)r * PC_MAX + k + 1); }
+          } else { v0 = a.tm[k]; v1 = has1 ? a.tm[k + 1] : 0.0; }
 #pragma unroll
           for (int q = 0; q < TR; q++) {
             const int row = i0 + q * G;
-            if (row >= m) continue;
-            // lower: k <= row ; upper: k >= row (the other triangle of the row-major factor holds zeros or garbage: mask)
-            const bool ok0 = pass ? (k >= row) : (k <= row), ok1 = pass ? (k + 1 >= row && k + 1 < m) : (k + 1 <= row);
-            if (!(ok0 || ok1)) continue;
-            const double2 w = *reinterpret_cast<const double2 *>(T + (int64_t)row * a.ldm + k);
-            acc[q] += (ok0 ? w.x * v0 : 0.0) + (ok1 ? w.y * v1 : 0.0);
+            const bool inr = row < m;
+            const double2 w = *reinterpret_cast<const double2 *>(a.Ginv + (inr ? (int64_t)row * a.ldm + k : 0));
+            acc[q] += (inr ? w.x * v0 : 0.0) + ((inr && has1) ? w.y * v1 : 0.0);
           }
         }
         cta_sum_multi<TR>(acc, red_d);
-        if (tid < TR && i0 + tid * G < m) out[i0 + tid * G] = acc[0];
+        if (tid < TR && i0 + tid * G < m) a.tu[i0 + tid * G] = acc[0];
       }
       grid.sync();
-      tick(3 + pass);
+      tick(3);
     }
     // ---- cols: gp = rp - J' u on the owned columns ; partials rp.gp, gp.gp
     {
@@ -345,19 +377,23 @@ __global__ void __launch_bounds__(FT, 1) fused_projcg_kernel(FusedArgs a) {
 
 // Returns 0 when the chunk was enqueued, 1 when this configuration is not eligible (the caller uses the unfused path).
 int fused_projcg_chunk(LargeState &S, int iters, int first, double *xs, double *r, double *dc, double *Ad, double *rp, double *gp) {
-  if (S.ineq || S.family != LFPSQP_FAM_DIAGQUAD || (S.n_loc & 1) || S.m < 1 || !S.fused_ok) return 1;
+  if (S.ineq || S.family != LFPSQP_FAM_DIAGQUAD || (S.n_loc & 1) || S.m < 1 || !S.fused_ok || !S.Ginv) return 1;
   if (S.world > 1 && !(S.comm && S.comm->peer_ready && S.m <= PC_MAX && S.world <= PC_RANKS)) return 1;
   FusedArgs a;
   for (int r = 0; r < PC_RANKS; r++) a.peer[r] = (S.world > 1) ? S.comm->peer_map[r] : nullptr;
   a.rank = S.rank; a.world = S.world; a.epoch = (S.world > 1) ? reinterpret_cast<unsigned long long *>(S.comm->peer_local + FZ_FLAG + PC_RANKS) : nullptr;   // lives with the region
   a.n = S.n_loc; a.ldj = S.ldj; a.ldm = S.ldm; a.m = S.m;
-  a.J = S.J; a.Linv = S.Linv; a.XT = S.XT; a.hd = S.hdiag;
-  a.xs = xs; a.dc = dc; a.r = r; a.Ad = Ad; a.rp = rp; a.gp = gp; a.tm = S.tm; a.ty = S.ty; a.tu = S.tu;
+  a.J = S.J; a.Ginv = S.Ginv; a.hd = S.hdiag;
+  a.xs = xs; a.dc = dc; a.r = r; a.Ad = Ad; a.rp = rp; a.gp = gp; a.tm = S.tm; a.tu = S.tu;
   a.part = S.fused_part; a.lp_rg = S.lp + 3 * (size_t)MAXP; a.np_rg = S.np_loop; a.first = first; a.max_iters = iters;
   a.ctrl = S.ctrl;
+  static const int rows_mode = getenv("LFPSQP_FUSED_ROWS") ? atoi(getenv("LFPSQP_FUSED_ROWS")) : 0;
+  a.rows_mode = rows_mode;
+  a.bar = reinterpret_cast<unsigned *>(S.fused_part + 3 * (size_t)S.fused_grid + 8);
+  cudaMemsetAsync(a.bar, 0, sizeof(unsigned), S.stream);
   static const bool want_prof = getenv("LFPSQP_FUSED_PROF") != nullptr;
   a.prof = want_prof ? S.fused_part + 3 * (size_t)S.fused_grid : nullptr;
-  const size_t smem = ((size_t)((S.m + 1) & ~1) + 2 * FT) * sizeof(double);
+  const size_t smem = ((size_t)((S.m + 1) & ~1) + 2 * FT + 4 * RCH) * sizeof(double);
   void *args[] = {&a};
   cudaError_t e = cudaLaunchCooperativeKernel((void *)fused_projcg_kernel, dim3(S.fused_grid), dim3(FT), args, smem, S.stream);
   if (e != cudaSuccess) { cudaGetLastError(); S.fused_ok = false; return 1; }
@@ -366,7 +402,7 @@ int fused_projcg_chunk(LargeState &S, int iters, int first, double *xs, double *
     double h[8];
     cudaMemcpyAsync(h, a.prof, sizeof(h), cudaMemcpyDeviceToHost, S.stream);
     cudaStreamSynchronize(S.stream);
-    fprintf(stderr, "[fused projcg] %d iterations max; us per phase over the chunk: hess %.1f | update1 %.1f | rows %.1f | tri1 %.1f | tri2 %.1f | cols %.1f | update3 %.1f\n",
+    fprintf(stderr, "[fused projcg] %d iterations max; us per phase over the chunk: hess %.1f | update1 %.1f | rows %.1f | solve %.1f | (unused %.1f) | cols %.1f | update3 %.1f\n",
             iters, h[0] / 1e3, h[1] / 1e3, h[2] / 1e3, h[3] / 1e3, h[4] / 1e3, h[5] / 1e3, h[6] / 1e3);
   }
   return 0;
@@ -377,8 +413,8 @@ void fused_projcg_init(LargeState &S, int device) {
   S.fused_ok = false;
   int coop = 0;
   if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) != cudaSuccess || !coop) { cudaGetLastError(); return; }
-  const size_t smem = ((size_t)((S.m + 1) & ~1) + 2 * FT) * sizeof(double);
-  if (smem > 200 * 1024) return;
+  const size_t smem = ((size_t)((S.m + 1) & ~1) + 2 * FT + 4 * RCH) * sizeof(double);
+  if (smem > 220 * 1024) return;
   if (cudaFuncSetAttribute(fused_projcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return; }
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_projcg_kernel, FT, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return; }
@@ -387,5 +423,8 @@ void fused_projcg_init(LargeState &S, int device) {
   if (cudaMalloc(&p, (3 * (size_t)S.fused_grid + 16) * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return; }
   cudaMemset(p, 0, (3 * (size_t)S.fused_grid + 16) * sizeof(double));
   S.owned.push_back(p); S.fused_part = (double *)p;
+  void *gi = nullptr;
+  if (cudaMalloc(&gi, (size_t)S.m * S.ldm * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return; }
+  S.owned.push_back(gi); S.Ginv = (double *)gi;
   S.fused_ok = true;
 }

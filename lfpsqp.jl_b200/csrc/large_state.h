@@ -25,6 +25,7 @@ struct LargeState {
   bool fused_ok = false;
   int fused_grid = 0;
   double *fused_part = nullptr;
+  double *Ginv = nullptr;                  // explicit G^-1 = L^-T L^-1 (m x m, symmetric) for the one-phase solve of the fused kernel
   int m = 0, sm_count = 148, world = 1, rank = 0;
   cudaStream_t stream = nullptr;
   lfpsqp_params prm;
