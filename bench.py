@@ -114,6 +114,14 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def _traffic(kernel, key):
+    """DRAM bytes of `kernel` from the committed ncu --set full capture (profiles/traffic.json), or None."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel][key])
+    except Exception:
+        return None
+
+
 def large_n_section(L, ctx, torch, dev, with_cpu, dist=None, rank=0, world=1, weak=False):
     """Secondary metric of BASELINE.json: large-n projcg iterations/s on config C5 (n=65536, m=2048 dense random
     diagonal-quadratic equality constraints, definition pinned in DESIGN.md), fixed-K projcg (tol=0) through the
@@ -177,9 +185,12 @@ def large_n_section(L, ctx, torch, dev, with_cpu, dist=None, rank=0, world=1, we
                       "n": n, "comm": {0: "none", 1: "NCCL", 2: "peer-memory all-reduce kernels (CUDA IPC over NVLink) + NCCL for the Gram"}[ctx.lib.lfpsqp_comm_mode(ctx.h)],
                       "l2": "J alone is 1 GiB per pass (>> 126 MB L2)"},
            "ms_per_iteration": ms_it, "gpu_launches_per_iteration": launches / K,
-           "roofline": {"bound": "hbm", "kernels": "rows_dot_kernel + cols_dot_kernel (+ tri_gemv, cg_update*)",
+           "roofline": {"bound": "hbm", "kernels": ("fused_projcg_kernel (persistent cooperative kernel: grid barriers, in-kernel peer-memory all-reduce)"
+                                                    if launches / K < 1.0 else "rows_dot_kernel + cols_dot_kernel (+ tri_gemv, cg_update*)"),
                         "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                        "algorithmic_bytes_per_iteration_per_gpu": bytes_it, "traffic": None,
+                        "algorithmic_bytes_per_iteration_per_gpu": bytes_it,
+                        "traffic": (_traffic("fused_projcg_kernel" if launches / K < 1.0 else "rows_dot_kernel+cols_dot_kernel", "bytes_per_iteration")
+                                    if (world == 1 and not weak) else None),
                         "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"}}
     try:
         dmma = ctx.fp64_peak("dmma")
@@ -445,7 +456,7 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     achieved = io_bytes / (kms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "batched_reg_kernel<SepReadmeIneq,2,1,true>", "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": _traffic("batched_reg_kernel", "bytes_per_launch"), "peak_source": peak_src,
                 "kernel_ms": kms,
                 "note": "per-instance state lives on-chip; HBM only sees I/O (%.0f B/instance), so HBM is NOT the binding "
                         "roof of this kernel: FP64 issue/latency is (see fp64)" % (io_bytes / B)}

@@ -18,16 +18,17 @@ struct LargeCtrl {
 
 // Peer-memory region every rank exports over CUDA IPC (comm.cu).  First part: pull-model all-reduce kernels of comm.cu
 // ([2][PC_MAX + PC_SCAL] doubles, parity double buffer; flags [PC_RANKS][PC_COLS] u64).  Second part (FZ_*): push-model
-// mailboxes of the persistent fused projcg kernel (large_fused.cu): every rank STORES its partial m-vector / scalars
-// into the slot [parity][its rank] of every peer's region and then its flag (release, system scope); consumers only
-// read local memory.
+// mailboxes of the persistent fused projcg kernel (large_fused.cu): 16-byte entries {value, exchange number}, one row
+// per source rank; every rank STORES its partial m-vector / scalars into the row [its rank] of every rank's region with
+// single 128-bit stores and consumers spin on the entries of their own (local) region.
 constexpr int PC_MAX = 8192, PC_SCAL = 32, PC_RANKS = 8, PC_COLS = 16;
 constexpr size_t PC_DATA = 2 * (size_t)(PC_MAX + PC_SCAL);
-constexpr size_t FZ_OFF = PC_DATA + (size_t)PC_RANKS * PC_COLS;              // doubles from the region start
-constexpr size_t FZ_VEC = FZ_OFF;                                           // [2][PC_RANKS][PC_MAX]
-constexpr size_t FZ_SCAL = FZ_VEC + 2 * (size_t)PC_RANKS * PC_MAX;          // [2][PC_RANKS][4]
-constexpr size_t FZ_FLAG = FZ_SCAL + 2 * (size_t)PC_RANKS * 4;              // [PC_RANKS] u64: last completed exchange of that rank
+constexpr size_t FZ_OFF = PC_DATA + (size_t)PC_RANKS * PC_COLS;              // doubles from the region start (16-byte aligned)
+constexpr size_t FZ_VEC = FZ_OFF;                                           // entries [PC_RANKS][PC_MAX]   (2 doubles each)
+constexpr size_t FZ_SCAL = FZ_VEC + 2 * (size_t)PC_RANKS * PC_MAX;          // entries [3 kinds][PC_RANKS]: d.Ad | rp.gp | gp.gp
+constexpr size_t FZ_FLAG = FZ_SCAL + 2 * (size_t)PC_RANKS * 4;              // (spare) [PC_RANKS] u64
 constexpr size_t PC_REGION_BYTES = (FZ_FLAG + PC_RANKS + 1) * 8;            // + this rank's exchange counter (u64)
+static_assert(FZ_OFF % 2 == 0 && FZ_SCAL % 2 == 0, "mailbox entries must be 16-byte aligned");
 
 // bound embedding of the large-n mode (kernels in large_ineq.cuh); device arrays, each nx doubles
 struct IneqDev {

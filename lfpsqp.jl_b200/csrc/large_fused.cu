@@ -55,49 +55,52 @@ struct FusedArgs {
   int rows_mode;
 };
 
-// ---- in-kernel all-reduce over NVLink (push model).  Exchange e uses the mailboxes of parity e & 1; rank s may push
-// exchange e + 2 only after it has seen every flag e + 1, and a rank raises its flag e + 1 only behind a grid barrier
-// that follows all of its reads of exchange e: the double buffer is race-free.
-__device__ __forceinline__ void st_sys(double *p, double v) { asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
-__device__ __forceinline__ void fz_raise(const FusedArgs &a, unsigned long long e) {   // CTA 0, threads < world: my flag -> every rank
-  if ((int)threadIdx.x < a.world) {
-    unsigned long long *f = reinterpret_cast<unsigned long long *>(a.peer[threadIdx.x] + FZ_FLAG) + a.rank;
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(e) : "memory");
-  }
+// ---- in-kernel all-reduce over NVLink: push model with flag-in-data mailboxes (the "LL" idea: every 16-byte entry
+// carries {value, exchange number} and is written with ONE 128-bit store, which the fabric delivers atomically; the
+// consumer spins on the entry itself).  No fence, no separate flag, no extra grid barrier: an exchange costs one
+// one-way NVLink latency.  Every rank (including the sender itself) receives a copy in its own region, so consumers
+// only read local memory; sums are taken in rank order => bitwise identical on every rank and CTA.
+// Reuse is safe without double buffering: a rank overwrites its entries of kind K only after it has consumed a later
+// exchange from every peer, and a peer sends that later exchange only behind a grid barrier that follows all of its
+// reads of kind K.
+struct __align__(16) LLEntry { double v; unsigned long long e; };
+__device__ __forceinline__ void ll_store(LLEntry *p, double v, unsigned long long e) {
+  asm volatile("st.relaxed.sys.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(e) : "memory");
 }
-// every CTA: wait until all ranks have raised flag e (local polling); false on a 4 s timeout (a peer died)
-__device__ __forceinline__ bool fz_wait(const FusedArgs &a, unsigned long long e, int *timeout_flag) {
+// spin until the entry carries exchange >= e; false after ~4 s (a peer died: do not hang the GPU)
+__device__ __forceinline__ bool ll_load(const LLEntry *p, unsigned long long e, double &v) {
+  long long bits; unsigned long long f;
+  const long long t0 = clock64();
+  do {
+    asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(bits), "=l"(f) : "l"(p) : "memory");
+    if (f >= e) { v = __longlong_as_double(bits); return true; }
+    __nanosleep(40);
+  } while (clock64() - t0 < 8000000000LL);
+  v = 0.0;
+  return false;
+}
+__device__ __forceinline__ LLEntry *ll_vec(double *region, int src_rank) { return reinterpret_cast<LLEntry *>(region + FZ_VEC) + (size_t)src_rank * PC_MAX; }
+__device__ __forceinline__ LLEntry *ll_scal(double *region, int kind, int src_rank) { return reinterpret_cast<LLEntry *>(region + FZ_SCAL) + kind * PC_RANKS + src_rank; }
+
+// all-reduce of nv <= 2 scalars of kinds kind0, kind0+1: `loc` is this rank's value (identical in every CTA).  CTA 0
+// pushes, every CTA polls its local mailboxes (threads r < world) and sums in rank order through shared memory.
+__device__ __forceinline__ bool fz_allreduce_scal(const FusedArgs &a, unsigned long long e, int kind0, const double *loc, int nv,
+                                                  double *out, double *shm /* >= 2 * PC_RANKS + 1 doubles */) {
+  __syncthreads();
+  if (threadIdx.x == 0) shm[2 * PC_RANKS] = 0.0;
+  if (blockIdx.x == 0 && (int)threadIdx.x < a.world)
+    for (int k = 0; k < nv; k++) ll_store(ll_scal(a.peer[threadIdx.x], kind0 + k, a.rank), loc[k], e);
+  __syncthreads();
   if ((int)threadIdx.x < a.world) {
-    const unsigned long long *f = reinterpret_cast<const unsigned long long *>(a.peer[a.rank] + FZ_FLAG) + threadIdx.x;
-    const long long t0 = clock64();
-    unsigned long long v;
-    do {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-      if (v >= e) break;
-      if (clock64() - t0 > 8000000000LL) { *timeout_flag = 1; break; }
-    } while (true);
+    for (int k = 0; k < nv; k++) {
+      double v;
+      if (!ll_load(ll_scal(a.peer[a.rank], kind0 + k, threadIdx.x), e, v)) shm[2 * PC_RANKS] = 1.0;
+      shm[k * PC_RANKS + threadIdx.x] = v;
+    }
   }
   __syncthreads();
-  return *timeout_flag == 0;
-}
-// all-reduce of nv <= 4 scalars: `loc` is this rank's value (identical in every CTA); returns the rank-ordered sums in out[]
-__device__ __forceinline__ bool fz_allreduce_scal(const FusedArgs &a, unsigned long long e, const double *loc, int nv, double *out,
-                                                  int *timeout_flag) {
-  if (blockIdx.x == 0) {
-    if ((int)threadIdx.x < a.world) {
-      double *dst = a.peer[threadIdx.x] + FZ_SCAL + ((e & 1) * PC_RANKS + a.rank) * 4;
-      for (int k = 0; k < nv; k++) st_sys(dst + k, loc[k]);
-    }
-    fz_raise(a, e);      // same thread, same peer: the release store orders the data stores before the flag
-  }
-  if (!fz_wait(a, e, timeout_flag)) return false;
-  const double *src = a.peer[a.rank] + FZ_SCAL + (e & 1) * PC_RANKS * 4;
-  for (int k = 0; k < nv; k++) {
-    double s = 0.0;
-    for (int r = 0; r < a.world; r++) s += __ldcg(src + r * 4 + k);   // mailboxes are written by remote GPUs: read at L2
-    out[k] = s;
-  }
-  return true;
+  for (int k = 0; k < nv; k++) { double s = 0.0; for (int r = 0; r < a.world; r++) s += shm[k * PC_RANKS + r]; out[k] = s; }
+  return shm[2 * PC_RANKS] == 0.0;
 }
 
 __device__ __forceinline__ double cta_sum_fixed(const double *p, int np, double *sh) {  // fixed-order sum, valid in every thread
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(FT, 1) fused_projcg_kernel(FusedArgs a) {
     tick(0);
     // ---- update1 (projcg.jl:74-93)
     dAd = cta_sum_fixed(pA, G, sh);
-    if (multi) { double o; if (!fz_allreduce_scal(a, ++ep, &dAd, 1, &o, &s_timeout)) { status = 5; break; } dAd = o; }
+    if (multi) { double o; if (!fz_allreduce_scal(a, ++ep, 0, &dAd, 1, &o, red_d)) { status = 5; break; } dAd = o; }
     iter++;
     if (dAd <= 0.0) { status = 2; break; }
     if (rg <= 0.0) { status = 3; break; }
@@ -252,20 +255,17 @@ __global__ void __launch_bounds__(FT, 1) fused_projcg_kernel(FusedArgs a) {
         acc = warp_sum(acc);
         if (lane == 0 && act) {
           if (!multi) a.tm[i] = acc;
-          else {  // push this rank's partial t_i into every rank's mailbox [parity][my rank]
-            const unsigned long long e = ep + 1;
-            for (int r = 0; r < a.world; r++) st_sys(a.peer[r] + FZ_VEC + ((e & 1) * PC_RANKS + a.rank) * (size_t)PC_MAX + i, acc);
+          else {  // push {partial t_i, exchange number} into every rank's mailbox row [my rank]: one 128-bit store per peer
+            for (int r = 0; r < a.world; r++) ll_store(ll_vec(a.peer[r], a.rank) + i, acc, ep + 1);
           }
         }
       }
     }
-    if (multi) __threadfence_system();
+    // t is complete behind a grid barrier; column-sharded, the remote partials are already on their way (no fence, no flag
+    // round trip) and the solve phase checks the per-entry exchange numbers.  (Without this barrier the early CTAs'
+    // polling competes with the CTAs still streaming J: measured slower.)
     grid.sync();
-    if (multi) {   // every CTA's pushes are ordered before the barrier: raise the flag, wait for everybody, then t = rank-ordered sum
-      ++ep;
-      if (c == 0) fz_raise(a, ep);
-      if (!fz_wait(a, ep, &s_timeout)) { status = 5; break; }
-    }
+    if (multi) ++ep;
     tick(2);
     // ---- u = G^-1 t with the explicit symmetric inverse G^-1 = L^-T L^-1 (formed once per factorisation by a DMMA
     // GEMM): ONE grid phase instead of two dependent triangular ones.  The CTA owns the rows c, c + G, ... and works
@@ -281,10 +281,31 @@ __global__ void __launch_bounds__(FT, 1) fused_projcg_kernel(FusedArgs a) {
           const int k = 2 * k2;
           const bool has1 = k + 1 < m;
           double v0, v1;
-          if (multi) {   // t = rank-ordered sum of the mailboxes (written by remote GPUs: read at L2)
-            const double *mb = a.peer[a.rank] + FZ_VEC + (ep & 1) * (size_t)PC_RANKS * PC_MAX;
+          if (multi) {   // t = rank-ordered sum of the mailbox entries (spin until each carries this exchange)
+            // first try: the entries of 4 ranks at a time with independent loads in flight (they have normally arrived
+            // behind the barrier); a late entry is then spun on individually.  Odd tail (k + 1 == m): re-read entry k.
             v0 = 0.0; v1 = 0.0;
-            for (int r = 0; r < a.world; r++) { v0 += __ldcg(mb + (size_t)r * PC_MAX + k); if (has1) v1 += __ldcg(mb + (size_t)r * PC_MAX + k + 1); }
+            const int k1 = has1 ? k + 1 : k;
+            for (int r0 = 0; r0 < a.world; r0 += 4) {
+              long long b0[4], b1[4]; unsigned long long f0[4], f1[4];
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                const int r = min(r0 + q, a.world - 1);
+                const LLEntry *mb = ll_vec(a.peer[a.rank], r);
+                asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(b0[q]), "=l"(f0[q]) : "l"(mb + k) : "memory");
+                asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(b1[q]), "=l"(f1[q]) : "l"(mb + k1) : "memory");
+              }
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                if (r0 + q < a.world) {
+                  const LLEntry *mb = ll_vec(a.peer[a.rank], r0 + q);
+                  double w0 = __longlong_as_double(b0[q]), w1 = __longlong_as_double(b1[q]);
+                  if (f0[q] < ep && !ll_load(mb + k, ep, w0)) s_timeout = 1;
+                  if (f1[q] < ep && !ll_load(mb + k1, ep, w1)) s_timeout = 1;
+                  v0 += w0; v1 += has1 ? w1 : 0.0;
+                }
+              }
+            }
           } else { v0 = a.tm[k]; v1 = has1 ? a.tm[k + 1] : 0.0; }
 #pragma unroll
           for (int q = 0; q < TR; q++) {
@@ -299,6 +320,7 @@ __global__ void __launch_bounds__(FT, 1) fused_projcg_kernel(FusedArgs a) {
       }
       grid.sync();
       tick(3);
+      if (multi && s_timeout) { status = 5; break; }
     }
     // ---- cols: gp = rp - J' u on the owned columns ; partials rp.gp, gp.gp
     {
@@ -346,7 +368,7 @@ __global__ void __launch_bounds__(FT, 1) fused_projcg_kernel(FusedArgs a) {
     gg = cta_sum_fixed(pC, G, sh);
     if (multi) {
       double loc[2] = {rpgp, gg}, o[2];
-      if (!fz_allreduce_scal(a, ++ep, loc, 2, o, &s_timeout)) { status = 5; break; }
+      if (!fz_allreduce_scal(a, ++ep, 1, loc, 2, o, red_d)) { status = 5; break; }
       rpgp = o[0]; gg = o[1];
     }
     beta = rpgp / rg;
