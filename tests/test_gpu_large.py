@@ -171,3 +171,47 @@ def test_exact_linesearch_large_vs_oracle(L, oracle):
     # nearly equal values: an iterate is only defined to that resolution, whatever the summation order of f
     assert rel(x, ox) <= max(1e-6, 10 * rel(fx, ox))
     assert abs(obj[-1] - oobj[-1]) <= max(1e-8, 10 * abs(fobj[-1] - oobj[-1]) / abs(oobj[-1])) * abs(oobj[-1])
+
+
+def _projcg_with(L, fused, n, m, seed, **kw):
+    import os
+    os.environ["LFPSQP_FUSED_PROJCG"] = "1" if fused else "0"     # read by lfpsqp_large_setup
+    try:
+        Q, A, b, xt, w, x0 = L.make_diagquad(n, m, seed=seed, cond=1e3)
+        P = L.LargeProblem(L.families.diagquad(Q, A, b, xt, w))
+        P.factor(x0, want=())
+        lam = np.random.default_rng(1).standard_normal(m) * 0.1
+        r = P.projcg(x0, lam=lam, **kw)
+        return r, P.ctx.last_launches
+    finally:
+        os.environ.pop("LFPSQP_FUSED_PROJCG", None)
+
+
+@pytest.mark.parametrize("n,m", [(2048, 96), (1000, 130), (770, 1), (20000, 512)])
+def test_fused_projcg_matches_multi_kernel_loop(L, n, m):
+    # large_fused.cu (one persistent cooperative kernel per chunk) vs the launch-per-phase loop: same projcg! (projcg.jl:40-121)
+    a, la = _projcg_with(L, False, n, m, 3, tol=1e-9, maxit=10000)
+    b, lb = _projcg_with(L, True, n, m, 3, tol=1e-9, maxit=10000)
+    assert lb < la / 20                                    # the fused path really ran (a handful of launches instead of 8 per iteration)
+    assert a["status"] == b["status"] == 1 and abs(a["iters"] - b["iters"]) <= 3 and b["nr"] < 1e-9
+    assert rel(b["sol"], a["sol"]) < 1e-10
+    a, _ = _projcg_with(L, False, n, m, 3, tol=0.0, maxit=7)
+    b, _ = _projcg_with(L, True, n, m, 3, tol=0.0, maxit=7)   # fixed iteration count: identical up to summation order
+    assert a["iters"] == b["iters"] == 7 and a["status"] == b["status"] == 4 and rel(b["sol"], a["sol"]) < 1e-13
+
+
+def test_fused_projcg_negative_curvature_and_full_solve(L, oracle):
+    import os
+    n, m = 2048, 96
+    Q, A, b, xt, w, x0 = L.make_diagquad(n, m, seed=11, cond=1e3)
+    lam2 = -50.0 * np.abs(np.random.default_rng(2).standard_normal(m))
+    out = []
+    for fused in (0, 1):
+        os.environ["LFPSQP_FUSED_PROJCG"] = str(fused)
+        try:
+            P = L.LargeProblem(L.families.diagquad(Q, A, b, xt, w)); P.factor(x0, want=())
+            out.append(P.projcg(x0, lam=lam2, tol=1e-20, maxit=10000))
+        finally:
+            os.environ.pop("LFPSQP_FUSED_PROJCG", None)
+    assert out[0]["status"] == out[1]["status"] == 2 and out[0]["iters"] == out[1]["iters"]      # projcg.jl:77-82
+    assert abs(np.linalg.norm(out[1]["sol"]) - 1.0) < 1e-12 and rel(out[1]["sol"], out[0]["sol"]) < 1e-9
