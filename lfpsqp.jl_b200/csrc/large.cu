@@ -70,9 +70,10 @@ static void gemm_nt(LargeState &S, int M, int N, int K, const double *A, int64_t
     ksplit = std::min(std::min(16, S.sm_count / tiles), K / 256);
     while (ksplit > 1 && (size_t)ksplit * M * N * 8 > S.gemm_ws_bytes) ksplit--;
     if (ksplit < 1) ksplit = 1;
-  } else if (mode == GEMM_ASSIGN && lower && K >= 8192 && tiles < 8 * S.sm_count) {
-    // wave quantisation of the big SYRK (C5: 136 lower tiles on 148 SMs = one wave at 92 %; C4: 528 tiles = 3.57 waves):
-    // split K so that tiles x ksplit fills whole waves (C5: 13 -> 1768 CTAs = 11.95 waves)
+  } else if (mode == GEMM_ASSIGN && lower && K >= 8192 && tiles < S.sm_count) {
+    // wave quantisation of a SYRK that does not fill one wave (C5: 136 lower tiles on 148 SMs = 92 %): split K so that
+    // tiles x ksplit fills whole waves (C5: 13 -> 1768 CTAs = 11.95 waves; measured 27.2 -> 28.9 TFLOP/s).  With several
+    // waves already (C4: 528 tiles) the split measured slower (7.6 -> 8.7 ms): not applied.
     auto eff = [&](int ks) { int64_t w = (int64_t)tiles * ks; return (double)w / (double)(((w + S.sm_count - 1) / S.sm_count) * S.sm_count); };
     int best = 1;
     for (int ks = 2; ks <= 16; ks++) {
@@ -439,6 +440,8 @@ static int run_pcg(lfpsqp_ctx *c, LargeState &S, double mu, double tol, int64_t 
   S.hctrl->tol = tol; S.hctrl->mu = mu; S.hctrl->pcg_iter = 0; S.hctrl->pcg_lim = (int)std::min<int64_t>(maxiter, 2000000000); S.hctrl->pcg_status = 0;
   write_ctrl_fields(S);
   int64_t k = 0;
+  // persistent fused path (large_fused.cu): the whole pcg! call is one cooperative launch
+  if (S.fused_ok && maxiter <= 128 && fused_pcg(S, dx, r, pv, z) == 0) return read_ctrl(c, S) ? -1 : 0;
   while (S.hctrl->pcg_status == 0) {
     for (int q = 0; q < S.pcg_chunk; q++, k++) {
       const int par = (int)(k & 1);
@@ -969,7 +972,7 @@ extern "C" int lfpsqp_large_setup(lfpsqp_ctx *c, int family, int64_t n_global, i
   CK(cudaStreamSynchronize(S.stream));
   {
     const char *env = getenv("LFPSQP_FUSED_PROJCG");   // "0" selects the multi-kernel projcg loop (A/B measurements, tests)
-    if (family == LFPSQP_FAM_DIAGQUAD && m > 0 && !(env && env[0] == '0')) fused_projcg_init(S, c->device);
+    if (family != LFPSQP_FAM_HOST && m > 0 && !(env && env[0] == '0')) fused_projcg_init(S, c->device);
   }
   return LFPSQP_OK;
 }

@@ -129,6 +129,87 @@ __device__ __forceinline__ void cta_sum_multi(double (&v)[NV], double *shm /* (F
   }
 }
 
+// ---- row phase shared by the fused projcg and pcg kernels: t[i] = J[i] . v for the rows of this CTA.  One WARP per
+// row (rows i = c + w G of warp w: every row of the CTA is streamed concurrently, so the bytes in flight stay constant
+// over the whole phase and all CTAs finish together); v goes through double-buffered shared-memory chunks (one L2
+// read per CTA instead of one per row); CU x 128-bit loads in flight per lane.  Single GPU: t -> a.tm.  Column-sharded:
+// {partial t_i, exchange number e} is pushed into every rank's mailbox row [my rank] with one 128-bit store per peer.
+__device__ __forceinline__ void fz_rows(const FusedArgs &a, const double *v, double2 *vch, bool multi, unsigned long long e) {
+  const int G = gridDim.x, c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, m = a.m;
+  const int64_t n2 = a.n >> 1;
+  const double2 *rp2 = reinterpret_cast<const double2 *>(v);
+  for (int pass0 = 0; c + (int64_t)pass0 * (FT / 32) * G < m; pass0++) {
+    const int i = c + (pass0 * (FT / 32) + warp) * G;
+    const bool act = i < m;
+    const double *row = a.J + (int64_t)(act ? i : 0) * a.ldj;
+    const int nch = (int)((n2 + RCH - 1) / RCH);
+    double acc = 0.0;
+    __syncthreads();
+    for (int p = tid; p < (int)min((int64_t)RCH, n2); p += FT) vch[p] = rp2[p];
+    __syncthreads();
+    for (int ch = 0; ch < nch; ch++) {
+      const double2 *cur = vch + (ch & 1) * RCH;
+      double2 *nxt = vch + ((ch + 1) & 1) * RCH;
+      const int64_t base = (int64_t)ch * RCH;
+      const int len = (int)min((int64_t)RCH, n2 - base);
+      if (ch + 1 < nch) {
+        const int nlen = (int)min((int64_t)RCH, n2 - base - RCH);
+        for (int p = tid; p < nlen; p += FT) nxt[p] = rp2[base + RCH + p];
+      }
+      if (act) {
+        const double *rb = row + 2 * base;
+        for (int p = lane; p < len; p += 32 * CU) {
+          double2 q[CU];
+#pragma unroll
+          for (int k = 0; k < CU; k++) { const int pp = p + k * 32; q[k] = (pp < len) ? ld_stream2(rb + 2 * pp) : make_double2(0.0, 0.0); }
+#pragma unroll
+          for (int k = 0; k < CU; k++) { const int pp = p + k * 32; if (pp < len) { const double2 w = cur[pp]; acc += q[k].x * w.x + q[k].y * w.y; } }
+        }
+      }
+      __syncthreads();
+    }
+    acc = warp_sum(acc);
+    if (lane == 0 && act) {
+      if (!multi) a.tm[i] = acc;
+      else for (int r = 0; r < a.world; r++) ll_store(ll_vec(a.peer[r], a.rank) + i, acc, e);
+    }
+  }
+}
+
+// ---- column phase shared by both kernels: s_j = sum_i J[i][j] u[i] over ALL m rows for the column pairs [p0, p1) this
+// CTA owns (u staged in shared memory `us`); thread groups split the rows, `fin(p, s0, s1)` is called once per pair by
+// its owner thread with the finished sums.
+template <class F>
+__device__ __forceinline__ void fz_cols(const FusedArgs &a, const double *us, double2 *red, int64_t p0, int64_t p1, F fin) {
+  const int tid = threadIdx.x, m = a.m;
+  for (int64_t pc = p0; pc < p1; pc += FT) {
+    const int PW = (int)min((int64_t)FT, p1 - pc);
+    const int RG = FT / PW;                       // row groups sharing one column pair
+    const int g = tid / PW, pl = tid - g * PW;
+    double a0 = 0.0, a1 = 0.0;
+    if (g < RG) {
+      const double *base = a.J + 2 * (pc + pl);
+      int i = g;
+      for (; i + (CU - 1) * RG < m; i += CU * RG) {
+        double2 q[CU];
+#pragma unroll
+        for (int k = 0; k < CU; k++) q[k] = ld_stream2(base + (int64_t)(i + k * RG) * a.ldj);
+#pragma unroll
+        for (int k = 0; k < CU; k++) { const double w = us[i + k * RG]; a0 += q[k].x * w; a1 += q[k].y * w; }
+      }
+      for (; i < m; i += RG) { const double2 q = ld_stream2(base + (int64_t)i * a.ldj); const double w = us[i]; a0 += q.x * w; a1 += q.y * w; }
+    }
+    __syncthreads();
+    red[tid] = make_double2(a0, a1);
+    __syncthreads();
+    if (g == 0) {
+      double s0 = 0.0, s1 = 0.0;
+      for (int k = 0; k < RG; k++) { const double2 w = red[k * PW + pl]; s0 += w.x; s1 += w.y; }
+      fin(pc + pl, s0, s1);
+    }
+  }
+}
+
 // Grid barrier of the cooperative launch: one monotone arrival counter (zeroed by the host before every launch);
 // thread 0 of each CTA arrives with a release-add at gpu scope and spins with acquire loads until everybody of this
 // generation has arrived.  Co-residency of all CTAs is guaranteed by cudaLaunchCooperativeKernel.
@@ -213,54 +294,8 @@ __global__ void __launch_bounds__(FT, 1) fused_projcg_kernel(FusedArgs a) {
     }
     grid.sync();
     tick(1);
-    // ---- rows: t[i] = J[i] . rp.  One WARP per row (rows i = c + w G of warp w: every row of the CTA is streamed
-    // concurrently, so the bytes in flight stay constant over the whole phase and all CTAs finish together); rp goes
-    // through double-buffered shared-memory chunks (one L2 read per CTA instead of one per row); CU x 128-bit loads
-    // in flight per lane.
-    {
-      const double2 *rp2 = reinterpret_cast<const double2 *>(a.rp);
-      for (int pass0 = 0; c + (int64_t)pass0 * (FT / 32) * G < m; pass0++) {
-        // rows_mode 0: rows c + w G (neighbouring CTAs stream neighbouring rows); 1: a contiguous block of rows per CTA
-        const int rpc = (m + G - 1) / G;
-        const int wq = pass0 * (FT / 32) + warp;
-        const int i = a.rows_mode ? (wq < rpc ? c * rpc + wq : m) : c + wq * G;
-        const bool act = i < m;
-        const double *row = a.J + (int64_t)(act ? i : 0) * a.ldj;
-        const int nch = (int)((n2 + RCH - 1) / RCH);
-        double acc = 0.0;
-        __syncthreads();
-        for (int p = tid; p < (int)min((int64_t)RCH, n2); p += FT) vch[p] = rp2[p];
-        __syncthreads();
-        for (int ch = 0; ch < nch; ch++) {
-          const double2 *cur = vch + (ch & 1) * RCH;
-          double2 *nxt = vch + ((ch + 1) & 1) * RCH;
-          const int64_t base = (int64_t)ch * RCH;
-          const int len = (int)min((int64_t)RCH, n2 - base);
-          if (ch + 1 < nch) {
-            const int nlen = (int)min((int64_t)RCH, n2 - base - RCH);
-            for (int p = tid; p < nlen; p += FT) nxt[p] = rp2[base + RCH + p];
-          }
-          if (act) {
-            const double *rb = row + 2 * base;
-            for (int p = lane; p < len; p += 32 * CU) {
-              double2 q[CU];
-#pragma unroll
-              for (int e = 0; e < CU; e++) { const int pp = p + e * 32; q[e] = (pp < len) ? ld_stream2(rb + 2 * pp) : make_double2(0.0, 0.0); }
-#pragma unroll
-              for (int e = 0; e < CU; e++) { const int pp = p + e * 32; if (pp < len) { const double2 v = cur[pp]; acc += q[e].x * v.x + q[e].y * v.y; } }
-            }
-          }
-          __syncthreads();
-        }
-        acc = warp_sum(acc);
-        if (lane == 0 && act) {
-          if (!multi) a.tm[i] = acc;
-          else {  // push {partial t_i, exchange number} into every rank's mailbox row [my rank]: one 128-bit store per peer
-            for (int r = 0; r < a.world; r++) ll_store(ll_vec(a.peer[r], a.rank) + i, acc, ep + 1);
-          }
-        }
-      }
-    }
+    // ---- rows: t = J rp (fz_rows: one warp per row; column-sharded: partials pushed into every rank's mailboxes)
+    fz_rows(a, a.rp, vch, multi, ep + 1);
     // t is complete behind a grid barrier; column-sharded, the remote partials are already on their way (no fence, no flag
     // round trip) and the solve phase checks the per-entry exchange numbers.  (Without this barrier the early CTAs'
     // polling competes with the CTAs still streaming J: measured slower.)
@@ -326,38 +361,13 @@ __global__ void __launch_bounds__(FT, 1) fused_projcg_kernel(FusedArgs a) {
     {
       for (int i = tid; i < m; i += FT) fsm[i] = a.tu[i];
       __syncthreads();
-      double2 *red = reinterpret_cast<double2 *>(red_d);
       double sb = 0.0, sc = 0.0;
-      for (int64_t pc = p0; pc < p1; pc += FT) {
-        const int PW = (int)min((int64_t)FT, p1 - pc);
-        const int RG = FT / PW;                       // row groups sharing one column pair
-        const int g = tid / PW, pl = tid - g * PW;
-        double a0 = 0.0, a1 = 0.0;
-        if (g < RG) {
-          const double *base = a.J + 2 * (pc + pl);
-          int i = g;
-          for (; i + (CU - 1) * RG < m; i += CU * RG) {
-            double2 q[CU];
-#pragma unroll
-            for (int e = 0; e < CU; e++) q[e] = ld_stream2(base + (int64_t)(i + e * RG) * a.ldj);
-#pragma unroll
-            for (int e = 0; e < CU; e++) { const double w = fsm[i + e * RG]; a0 += q[e].x * w; a1 += q[e].y * w; }
-          }
-          for (; i < m; i += RG) { const double2 q = ld_stream2(base + (int64_t)i * a.ldj); const double w = fsm[i]; a0 += q.x * w; a1 += q.y * w; }
-        }
-        __syncthreads();
-        red[tid] = make_double2(a0, a1);
-        __syncthreads();
-        if (g == 0) {
-          double s0 = 0.0, s1 = 0.0;
-          for (int e = 0; e < RG; e++) { const double2 v = red[e * PW + pl]; s0 += v.x; s1 += v.y; }
-          const int64_t p = pc + pl;
-          const double2 rp2 = *reinterpret_cast<const double2 *>(a.rp + 2 * p);
-          const double2 g2 = make_double2(rp2.x - s0, rp2.y - s1);
-          *reinterpret_cast<double2 *>(a.gp + 2 * p) = g2;
-          sb += rp2.x * g2.x + rp2.y * g2.y; sc += g2.x * g2.x + g2.y * g2.y;
-        }
-      }
+      fz_cols(a, fsm, reinterpret_cast<double2 *>(red_d), p0, p1, [&](int64_t p, double s0, double s1) {
+        const double2 rp2 = *reinterpret_cast<const double2 *>(a.rp + 2 * p);
+        const double2 g2 = make_double2(rp2.x - s0, rp2.y - s1);
+        *reinterpret_cast<double2 *>(a.gp + 2 * p) = g2;
+        sb += rp2.x * g2.x + rp2.y * g2.y; sc += g2.x * g2.x + g2.y * g2.y;
+      });
       sb = block_sum(sb, sh); sc = block_sum(sc, sh);
       if (tid == 0) { pB[c] = sb; pC[c] = sc; }
     }
@@ -392,6 +402,109 @@ __global__ void __launch_bounds__(FT, 1) fused_projcg_kernel(FusedArgs a) {
     if (status == 5) ctrl->rankflag = 99;
     ctrl->iter = iter; ctrl->status = status; ctrl->dAd = dAd; ctrl->alpha = alpha; ctrl->beta = beta;
     ctrl->rpgp = rpgp; ctrl->gg = gg; ctrl->rg = rg; ctrl->nr = nr;
+  }
+}
+
+
+// ================================================================== persistent pcg! (src/retractions.jl:179-246, M! = copy)
+// CG on (J'J + mu I) dx = r inside ProjPenalty's Gauss-Newton step: the other HBM-bound loop of the large-n mode (two
+// passes over J per iteration, no solve).  Same building blocks as the projcg kernel; the whole pcg! call (at most
+// maxiter_pcg <= 128 iterations) is ONE launch.  Vector roles in FusedArgs: xs = dx, r = r, dc = p, Ad = z.
+//   rho_k = r.r ; exit tests (||r|| <= tol, iteration cap) ; p = r + (rho_k / rho_{k-1}) p      [owned columns]   (:207-216)
+//   B   t = J p                                                                                  [owned rows]      (:221)
+//   B   z = J' t + mu p ; partial p.z                                                            [owned columns]   (:222-226)
+//   B   alpha = rho / p.z ; dx += alpha p ; r -= alpha z ; partial r.r                           [owned columns]   (:229-235)
+//   B
+__global__ void __launch_bounds__(FT, 1) fused_pcg_kernel(FusedArgs a) {
+  GridBar grid{a.bar, 0u, gridDim.x};
+  extern __shared__ __align__(16) double fsm[];
+  __shared__ double sh[33];
+  const int G = gridDim.x, c = blockIdx.x, tid = threadIdx.x, m = a.m;
+  const int64_t n2 = a.n >> 1;
+  const int64_t P = (n2 + G - 1) / G;
+  const int64_t p0 = min((int64_t)c * P, n2), p1 = min(p0 + P, n2);
+  double *pA = a.part, *pB = a.part + G;
+  double *red_d = fsm + ((m + 1) & ~1);
+  double2 *vch = reinterpret_cast<double2 *>(red_d + 2 * FT);
+  LargeCtrl *ctrl = a.ctrl;
+  const bool multi = a.world > 1;
+  unsigned long long ep = multi ? *a.epoch : 0ULL;
+  const double tol = ctrl->tol, mu = ctrl->mu;
+  const int lim = ctrl->pcg_lim;
+  int iter = 0, status = 0;
+  double rho = cta_sum_fixed(a.lp_rg, a.np_rg, sh), rho_prev = 1.0, norm_res = INFINITY, pz = 0.0, alpha = 0.0;
+  grid.sync();
+  if (multi) { double o; if (!fz_allreduce_scal(a, ++ep, 1, &rho, 1, &o, red_d)) status = 5; rho = o; }
+  while (status == 0) {
+    // ---- :207-216
+    if (!(norm_res > tol)) { status = 1; break; }
+    if (iter >= lim) { status = 4; break; }
+    const double beta = rho / rho_prev;
+    for (int64_t p = p0 + tid; p < p1; p += FT) {
+      const double2 r2 = *reinterpret_cast<const double2 *>(a.r + 2 * p);
+      double2 d2 = *reinterpret_cast<double2 *>(a.dc + 2 * p);
+      d2.x = r2.x + beta * d2.x; d2.y = r2.y + beta * d2.y;
+      *reinterpret_cast<double2 *>(a.dc + 2 * p) = d2;
+    }
+    grid.sync();
+    // ---- t = J p
+    fz_rows(a, a.dc, vch, multi, ep + 1);
+    grid.sync();
+    if (multi) ++ep;
+    // ---- z = J' t + mu p ; partial p.z
+    {
+      bool late = false;
+      for (int i = tid; i < m; i += FT) {
+        double s;
+        if (multi) {
+          s = 0.0;
+          for (int r = 0; r < a.world; r++) { double w; if (!ll_load(ll_vec(a.peer[a.rank], r) + i, ep, w)) late = true; s += w; }
+        } else s = a.tm[i];
+        fsm[i] = s;
+      }
+      if (__syncthreads_or(late)) { status = 5; break; }
+      double sp = 0.0;
+      fz_cols(a, fsm, reinterpret_cast<double2 *>(red_d), p0, p1, [&](int64_t p, double s0, double s1) {
+        const double2 d2 = *reinterpret_cast<const double2 *>(a.dc + 2 * p);
+        const double2 z2 = make_double2(s0 + mu * d2.x, s1 + mu * d2.y);
+        *reinterpret_cast<double2 *>(a.Ad + 2 * p) = z2;
+        sp += d2.x * z2.x + d2.y * z2.y;
+      });
+      sp = block_sum(sp, sh);
+      if (tid == 0) pA[c] = sp;
+    }
+    grid.sync();
+    pz = cta_sum_fixed(pA, G, sh);
+    if (multi) { double o; if (!fz_allreduce_scal(a, ++ep, 0, &pz, 1, &o, red_d)) { status = 5; break; } pz = o; }
+    // ---- :229-235
+    alpha = rho / pz;
+    {
+      double sr = 0.0;
+      for (int64_t p = p0 + tid; p < p1; p += FT) {
+        const double2 d2 = *reinterpret_cast<const double2 *>(a.dc + 2 * p);
+        const double2 z2 = *reinterpret_cast<const double2 *>(a.Ad + 2 * p);
+        double2 x2 = *reinterpret_cast<double2 *>(a.xs + 2 * p);
+        double2 r2 = *reinterpret_cast<double2 *>(a.r + 2 * p);
+        x2.x += alpha * d2.x; x2.y += alpha * d2.y;
+        r2.x -= alpha * z2.x; r2.y -= alpha * z2.y;
+        *reinterpret_cast<double2 *>(a.xs + 2 * p) = x2;
+        *reinterpret_cast<double2 *>(a.r + 2 * p) = r2;
+        sr += r2.x * r2.x + r2.y * r2.y;
+      }
+      sr = block_sum(sr, sh);
+      if (tid == 0) pB[c] = sr;
+    }
+    grid.sync();
+    rho_prev = rho;
+    rho = cta_sum_fixed(pB, G, sh);
+    if (multi) { double o; if (!fz_allreduce_scal(a, ++ep, 1, &rho, 1, &o, red_d)) { status = 5; break; } rho = o; }
+    norm_res = sqrt(rho);
+    iter++;
+  }
+  if (c == 0 && tid == 0) {
+    if (multi) *a.epoch = ep;
+    if (status == 5) ctrl->rankflag = 99;
+    ctrl->pcg_iter = iter; ctrl->pcg_status = status; ctrl->norm_res = norm_res; ctrl->rho = rho; ctrl->pz = pz; ctrl->alpha = alpha;
   }
 }
 
@@ -430,6 +543,30 @@ int fused_projcg_chunk(LargeState &S, int iters, int first, double *xs, double *
   return 0;
 }
 
+// The whole pcg! call as one launch (state as large.cu::run_pcg: dx = S.w3, r = S.w0, p = S.w1 zeroed, z = S.w2, r.r partials of
+// the start residual in loop slot 5; tol / mu / pcg_lim already in the device control block).  Returns 1 when not eligible.
+int fused_pcg(LargeState &S, double *dx, double *r, double *pv, double *z) {
+  if (S.ineq || (S.n_loc & 1) || S.m < 1 || !S.fused_ok) return 1;
+  if (S.world > 1 && !(S.comm && S.comm->peer_ready && S.m <= PC_MAX && S.world <= PC_RANKS)) return 1;
+  FusedArgs a;
+  for (int q = 0; q < PC_RANKS; q++) a.peer[q] = (S.world > 1) ? S.comm->peer_map[q] : nullptr;
+  a.rank = S.rank; a.world = S.world;
+  a.epoch = (S.world > 1) ? reinterpret_cast<unsigned long long *>(S.comm->peer_local + FZ_FLAG + PC_RANKS) : nullptr;
+  a.n = S.n_loc; a.ldj = S.ldj; a.ldm = S.ldm; a.m = S.m;
+  a.J = S.J; a.Ginv = nullptr; a.hd = nullptr;
+  a.xs = dx; a.dc = pv; a.r = r; a.Ad = z; a.rp = nullptr; a.gp = nullptr; a.tm = S.tm; a.tu = S.tu;
+  a.part = S.fused_part; a.lp_rg = S.lp + 5 * (size_t)MAXP; a.np_rg = S.np_loop_raw; a.first = 1; a.max_iters = 0;
+  a.ctrl = S.ctrl; a.prof = nullptr; a.rows_mode = 0;
+  a.bar = reinterpret_cast<unsigned *>(S.fused_part + 3 * (size_t)S.fused_grid + 8);
+  cudaMemsetAsync(a.bar, 0, sizeof(unsigned), S.stream);
+  const size_t smem = ((size_t)((S.m + 1) & ~1) + 2 * FT + 4 * RCH) * sizeof(double);
+  void *args[] = {&a};
+  cudaError_t e = cudaLaunchCooperativeKernel((void *)fused_pcg_kernel, dim3(S.fused_grid), dim3(FT), args, smem, S.stream);
+  if (e != cudaSuccess) { cudaGetLastError(); return 1; }
+  S.launches++;
+  return 0;
+}
+
 // one-time eligibility probe: cooperative launch support, co-residency of one CTA per SM with the dynamic shared memory
 void fused_projcg_init(LargeState &S, int device) {
   S.fused_ok = false;
@@ -438,6 +575,7 @@ void fused_projcg_init(LargeState &S, int device) {
   const size_t smem = ((size_t)((S.m + 1) & ~1) + 2 * FT + 4 * RCH) * sizeof(double);
   if (smem > 220 * 1024) return;
   if (cudaFuncSetAttribute(fused_projcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return; }
+  if (cudaFuncSetAttribute(fused_pcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return; }
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_projcg_kernel, FT, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return; }
   S.fused_grid = S.sm_count;
@@ -445,8 +583,10 @@ void fused_projcg_init(LargeState &S, int device) {
   if (cudaMalloc(&p, (3 * (size_t)S.fused_grid + 16) * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return; }
   cudaMemset(p, 0, (3 * (size_t)S.fused_grid + 16) * sizeof(double));
   S.owned.push_back(p); S.fused_part = (double *)p;
-  void *gi = nullptr;
-  if (cudaMalloc(&gi, (size_t)S.m * S.ldm * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return; }
-  S.owned.push_back(gi); S.Ginv = (double *)gi;
+  if (S.family == LFPSQP_FAM_DIAGQUAD) {   // explicit G^-1 is only needed by the fused projcg (diagonal Hessians); pcg needs no factor
+    void *gi = nullptr;
+    if (cudaMalloc(&gi, (size_t)S.m * S.ldm * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return; }
+    S.owned.push_back(gi); S.Ginv = (double *)gi;
+  }
   S.fused_ok = true;
 }

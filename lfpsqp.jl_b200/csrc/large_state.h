@@ -62,6 +62,7 @@ struct LargeState {
 
 // large_fused.cu: one cooperative kernel per chunk of projcg iterations (returns 1 when not eligible -> unfused path)
 int fused_projcg_chunk(LargeState &S, int iters, int first, double *xs, double *r, double *dc, double *Ad, double *rp, double *gp);
+int fused_pcg(LargeState &S, double *dx, double *r, double *pv, double *z);   // the whole pcg! call as one launch
 void fused_projcg_init(LargeState &S, int device);
 
 // comm.cu

@@ -43,6 +43,18 @@ for fused in (0, 1):
     P = L.LargeProblem(L.families.diagquad(Q, A, b, xt, w))
     t0 = time.time(); x, obj, lam, info, st, status = P.solve(x0, L.LFPSQPParams(), return_stats=True); t1 = time.time()
     print("solve fused=%d iter %d cond %d f %.15e cg %d  %.3fs" % (fused, info.iter, int(info.condition), obj[-1], st["projcg_iters"], t1 - t0), flush=True)
+# pcg! (retractions.jl:179-246): fused one-launch kernel vs the multi-kernel loop
+for (n, m) in [(2048, 96), (1000, 130), (20000, 512)]:
+    res = []
+    for fused in (0, 1):
+        os.environ["LFPSQP_FUSED_PROJCG"] = str(fused)
+        Q, A, b, xt, w, x0 = L.make_diagquad(n, m, seed=3, cond=1e3)
+        P = L.LargeProblem(L.families.diagquad(Q, A, b, xt, w))
+        rhs = np.random.default_rng(5).standard_normal(n)
+        res.append(P.pcg(x0, 1e-2, rhs, tol=1e-8, maxiter=100) + (P.ctx.last_launches,))
+    (xa, ra, fa, ia, la), (xb, rb, fb, ib, lb) = res
+    print("pcg n=%d m=%d: iters %d/%d flag %d/%d x rel diff %.2e |r| %.2e/%.2e launches %d/%d" % (
+        n, m, ia, ib, fa, fb, rel(xb, xa), np.linalg.norm(ra), np.linalg.norm(rb), la, lb), flush=True)
 # C5 timing
 if len(sys.argv) > 1:
     import torch
@@ -51,3 +63,18 @@ if len(sys.argv) > 1:
         a, la = run(n, m, 0, bool(fused), K=K, reps=4)
         print("C5 fused=%d: %.1f us/iteration (%.0f it/s), launches %d, roofline frac vs 6650 GB/s %.3f" % (
             fused, 1e3 * a["ms"] / K, K / a["ms"] * 1e3, la, (16.0 * m * n + 8.0 * m * m + 104.0 * n) / (a["ms"] / K * 1e-3) / 6650e9), flush=True)
+    # pcg at C5: wall time of the unit-level call minus its setup (jac + H2D) measured with maxiter = 0
+    for fused in (0, 1):
+        os.environ["LFPSQP_FUSED_PROJCG"] = str(fused)
+        Q, A, b, xt, w, x0 = L.make_diagquad(n, m, seed=0, cond=1e3)
+        P = L.LargeProblem(L.families.diagquad(Q, A, b, xt, w))
+        rhs = np.random.default_rng(5).standard_normal(n)
+        def timed(mi):
+            best = 1e9
+            for _ in range(3):
+                t0 = time.perf_counter(); out = P.pcg(x0, 1e-2, rhs, tol=0.0, maxiter=mi); best = min(best, time.perf_counter() - t0)
+            return best, out
+        t0_, _ = timed(0); t1_, out = timed(100)
+        per = (t1_ - t0_) / 100
+        print("C5 pcg fused=%d: %.1f us/iteration (%.0f it/s), iters %d, roofline frac vs 6650 GB/s %.3f" % (
+            fused, per * 1e6, 1 / per, out[3], (16.0 * m * n + 88.0 * n) / per / 6650e9), flush=True)
