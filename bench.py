@@ -170,6 +170,22 @@ def large_n_section(L, ctx, torch, dev, with_cpu, dist=None, rank=0, world=1, we
         per.append(ms / K)
         launches = ctx.last_launches
     ms_it = float(np.median(per))
+    # the retraction's inner loop: pcg! (retractions.jl:179-246) on (J'J + mu I) dx = b, fixed 100 iterations (tol = 0)
+    rhs = np.random.default_rng(5 + rank).standard_normal(nloc)
+    pcg_per = []
+    pcg_launches = 0
+    for rep in range(4):
+        if world > 1:
+            dist.barrier()
+        _, _, _, pit = P.pcg(x0h, 1e-2, rhs, tol=0.0, maxiter=100)
+        ms = ctx.last_kernel_ms / max(pit, 1) * 100.0    # normally all 100 iterations run (tol = 0)
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
+        if rep > 0:
+            pcg_per.append(ms / 100)
+        pcg_launches = ctx.last_launches
+    pcg_ms = float(np.median(pcg_per))
+    pcg_bytes = 16.0 * m * nloc + 96.0 * nloc     # two passes over J + 12 vector sweeps (p, r, z, dx)
     bytes_it = 16.0 * m * nloc + 8.0 * m * m + 104.0 * nloc   # per GPU; SURVEY.md 8(d): two passes over J + two triangular GEMVs + vector sweeps
     peaks = {}
     try:
@@ -192,6 +208,13 @@ def large_n_section(L, ctx, torch, dev, with_cpu, dist=None, rank=0, world=1, we
                         "traffic": (_traffic("fused_projcg_kernel" if launches / K < 1.0 else "rows_dot_kernel+cols_dot_kernel", "bytes_per_iteration")
                                     if (world == 1 and not weak) else None),
                         "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"}}
+    out["retraction_pcg"] = {"metric": "ProjPenalty pcg! iterations/s (retractions.jl:179-246)", "value": 1e3 / pcg_ms, "unit": "iterations/s",
+                             "ms_per_iteration": pcg_ms, "gpu_launches_per_iteration": pcg_launches / 100.0,
+                             "roofline": {"bound": "hbm", "kernel": ("fused_pcg_kernel (one cooperative launch per pcg! call)" if pcg_launches < 50
+                                                                     else "pcg_a + rows_dot + cols_dot + pcg_z + pcg_x"),
+                                          "achieved": pcg_bytes / (pcg_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                          "frac": pcg_bytes / (pcg_ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes_per_iteration_per_gpu": pcg_bytes,
+                                          "traffic": None}}
     try:
         dmma = ctx.fp64_peak("dmma")
         flops = float(m) * (m + 1) * nloc

@@ -1195,12 +1195,15 @@ extern "C" int lfpsqp_large_pcg(lfpsqp_ctx *c, const double *x_point_loc, double
   S.reset_counters();
   fam_c_jac(S, S.J, S.cval, S.x);
   pcg_start_kernel<<<S.vgrid, 256, 0, S.stream>>>(n, r, dx, pv, lp);
+  cudaEventRecord(c->ev0, S.stream);
   if (run_pcg(c, S, mu, tol, maxiter)) return LFPSQP_ERR_CUDA;
+  cudaEventRecord(c->ev1, S.stream);
   if (x_out_loc) CK(cudaMemcpyAsync(x_out_loc, dx, n * 8, cudaMemcpyDeviceToHost, S.stream));
   if (r_out_loc) CK(cudaMemcpyAsync(r_out_loc, r, n * 8, cudaMemcpyDeviceToHost, S.stream));
   CK(cudaStreamSynchronize(S.stream));
   if (iters) *iters = S.hctrl->pcg_iter;
   if (flag) *flag = (S.hctrl->pcg_iter == maxiter) ? 1 : 0;
+  { float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->last_ms = ms; }   // device time of the pcg! loop (lfpsqp_last_kernel_ms)
   c->last_launches = S.launches;
   return LFPSQP_OK;
 }

@@ -215,3 +215,25 @@ def test_fused_projcg_negative_curvature_and_full_solve(L, oracle):
             os.environ.pop("LFPSQP_FUSED_PROJCG", None)
     assert out[0]["status"] == out[1]["status"] == 2 and out[0]["iters"] == out[1]["iters"]      # projcg.jl:77-82
     assert abs(np.linalg.norm(out[1]["sol"]) - 1.0) < 1e-12 and rel(out[1]["sol"], out[0]["sol"]) < 1e-9
+
+
+@pytest.mark.parametrize("n,m", [(2048, 96), (1000, 130), (20000, 512)])
+def test_fused_pcg_matches_multi_kernel_loop(L, n, m):
+    # pcg! (retractions.jl:179-246) as ONE cooperative launch (large_fused.cu) vs the launch-per-phase loop
+    import os
+    res = []
+    for fused in (0, 1):
+        os.environ["LFPSQP_FUSED_PROJCG"] = str(fused)
+        try:
+            Q, A, b, xt, w, x0 = L.make_diagquad(n, m, seed=3, cond=1e3)
+            P = L.LargeProblem(L.families.diagquad(Q, A, b, xt, w))
+            rhs = np.random.default_rng(5).standard_normal(n)
+            res.append(P.pcg(x0, 1e-2, rhs, tol=1e-8, maxiter=100) + (P.ctx.last_launches,))
+        finally:
+            os.environ.pop("LFPSQP_FUSED_PROJCG", None)
+    (xa, ra, fa, ia, la), (xb, rb, fb, ib, lb) = res
+    assert lb <= 4 < la and ia == ib and fa == fb == 0
+    assert rel(xb, xa) < 1e-12 and np.linalg.norm(rb) <= 1e-8
+    # the solution really solves (J'J + mu I) x = b
+    J = Q * x0[None, :] + A
+    assert np.linalg.norm(J.T @ (J @ xb) + 1e-2 * xb - rhs) < 1e-7
