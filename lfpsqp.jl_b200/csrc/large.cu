@@ -972,7 +972,7 @@ extern "C" int lfpsqp_large_setup(lfpsqp_ctx *c, int family, int64_t n_global, i
   CK(cudaStreamSynchronize(S.stream));
   {
     const char *env = getenv("LFPSQP_FUSED_PROJCG");   // "0" selects the multi-kernel projcg loop (A/B measurements, tests)
-    if (family != LFPSQP_FAM_HOST && m > 0 && !(env && env[0] == '0')) fused_projcg_init(S, c->device);
+    if (m > 0 && !(env && env[0] == '0')) fused_projcg_init(S, c->device);   // pcg! is fused for every family, projcg for diagonal Hessians
   }
   return LFPSQP_OK;
 }

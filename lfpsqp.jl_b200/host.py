@@ -132,20 +132,12 @@ def optimize_explicit(f, grad, c, jac, hess_lag_vec, x0, xl, xu, m, param=None, 
     return res
 
 
-def optimize_slack(f, grad, hess_vec, c, jac, chess_vec, d, djac, dhess_vec, dl, du, x0, xl, xu, m, p, param=None, **kw):
-    """The slack wrapper optimize(f, c!, d!, dl, du, x0, xl, xu, m, p, param) (src/optimize.jl:13-71) with explicit
-    derivatives in place of the reference's AD:  x_aux = [x ; s], s0 = d(x0), bounds [xl ; dl] <= x_aux <= [xu ; du],
-    constraints [c(x) ; d(x) - s].
-        hess_vec(dest, src, x): dest = Hess f(x) src ;  chess_vec / dhess_vec(dest, src, x, lam): dest = sum_i lam_i Hess c_i src
-        c(cval, x), jac(Jc, cval, x) / d(dval, x), djac(Jd, dval, x): as the reference (may be None when m == 0)"""
+def slack_callbacks(f, grad, hess_vec, c, jac, chess_vec, d, djac, dhess_vec, dl, du, x0, xl, xu, m, p):
+    """The augmented problem of the slack wrapper (src/optimize.jl:23-51) with explicit derivatives in place of the
+    reference's AD: returns (f_aux, grad_aux, c_aux, jac_aux, hess_aux, x0_aux, xl_aux, xu_aux) for
+    x_aux = [x ; s], s0 = d(x0), bounds [xl ; dl] <= x_aux <= [xu ; du], constraints [c(x) ; d(x) - s]."""
     x0 = np.asarray(x0, dtype=np.float64)
     n = x0.size
-    if d is None or p == 0:                                                               # optimize.jl:15-17
-        def hl(dest, src, x, lam):
-            hess_vec(dest, src, x)
-            if m > 0:
-                t = np.zeros(n); chess_vec(t, src, x, lam); dest += t
-        return optimize_explicit(f, grad, c, jac, hl, x0, xl, xu, m, param, **kw)
     dl = np.asarray(dl, dtype=np.float64); du = np.asarray(du, dtype=np.float64)
     if not (len(dl) == len(du) == p):
         raise _lib.LFPSQPError("Bound vectors dl and du must be of size p")               # optimize.jl:19-21
@@ -181,5 +173,23 @@ def optimize_slack(f, grad, hess_vec, c, jac, chess_vec, d, djac, dhess_vec, dl,
             t[:] = 0.0; chess_vec(t, src[:n], x[:n], lam[:m]); dest[:n] += t
         t[:] = 0.0; dhess_vec(t, src[:n], x[:n], lam[m:]); dest[:n] += t
 
+    return f_aux, grad_aux, c_aux, jac_aux, hess_aux, x0a, xla, xua
+
+
+def optimize_slack(f, grad, hess_vec, c, jac, chess_vec, d, djac, dhess_vec, dl, du, x0, xl, xu, m, p, param=None, **kw):
+    """The slack wrapper optimize(f, c!, d!, dl, du, x0, xl, xu, m, p, param) (src/optimize.jl:13-71) with explicit
+    derivatives in place of the reference's AD (see slack_callbacks).
+        hess_vec(dest, src, x): dest = Hess f(x) src ;  chess_vec / dhess_vec(dest, src, x, lam): dest = sum_i lam_i Hess c_i src
+        c(cval, x), jac(Jc, cval, x) / d(dval, x), djac(Jd, dval, x): as the reference (may be None when m == 0)"""
+    x0 = np.asarray(x0, dtype=np.float64)
+    n = x0.size
+    if d is None or p == 0:                                                               # optimize.jl:15-17
+        def hl(dest, src, x, lam):
+            hess_vec(dest, src, x)
+            if m > 0:
+                t = np.zeros(n); chess_vec(t, src, x, lam); dest += t
+        return optimize_explicit(f, grad, c, jac, hl, x0, xl, xu, m, param, **kw)
+    f_aux, grad_aux, c_aux, jac_aux, hess_aux, x0a, xla, xua = slack_callbacks(f, grad, hess_vec, c, jac, chess_vec, d, djac,
+                                                                                 dhess_vec, dl, du, x0, xl, xu, m, p)
     out = optimize_explicit(f_aux, grad_aux, c_aux, jac_aux, hess_aux, x0a, xla, xua, m + p, param, **kw)
     return (out[0][:n],) + tuple(out[1:])                                                # :67-70 (lambda untruncated)

@@ -27,3 +27,23 @@ if mode in ("all", "large"):
     P = L.LargeProblem(L.families.diagquad(Q, A, b, xt, w))
     print(P.solve(x0, L.LFPSQPParams(maxiter=3))[3])
     print(P.solve(x0, L.LFPSQPParams(maxiter=2, do_project_retract=False))[3])
+if mode in ("all", "new"):
+    # round-1 additions: bounds in large-n mode, host callbacks, fused projcg / pcg kernels (cooperative launch)
+    Q, A, b, xt, w, x0 = L.make_diagquad(64, 4, seed=5, cond=50.0)
+    fam = L.families.diagquad(Q, A, b, xt, w)
+    P = L.LargeProblem(fam)
+    P.set_bounds(x0 - 0.5, x0 + 0.7)
+    print(P.solve(x0, L.LFPSQPParams(maxiter=3))[3])
+    print(P.solve(x0, L.LFPSQPParams(maxiter=2, do_project_retract=False))[3])
+    P.set_bounds(None, None)
+    print(P.solve(x0, L.LFPSQPParams(maxiter=3))[3])            # fused projcg + fused pcg
+    P.factor(x0, want=())
+    print(P.projcg(x0, lam=np.zeros(4), tol=1e-8, maxit=50)["iters"], P.pcg(x0, 1e-2, np.ones(64), tol=1e-8, maxiter=50)[3])
+    def f(x): return 0.5 * np.sum(w * (x - xt) ** 2)
+    def grad(g, x): g[:] = w * (x - xt)
+    def c(cv, x): cv[:] = 0.5 * Q @ (x * x) + A @ x - b
+    def jac(Jc, cv, x): Jc[:, :] = Q * x[None, :] + A; c(cv, x)
+    def hlv(dest, src, x, lam): dest[:] = (w + Q.T @ lam) * src
+    print(L.optimize(f, grad, c, jac, hlv, x0, x0 - 0.5, x0 + 0.7, 4, L.LFPSQPParams(maxiter=3))[3])
+    Q, A, b, xt, w, x0 = L.make_diagquad(65, 3, seed=6, cond=50.0)   # odd n through the callbacks
+    print(L.optimize(f, grad, c, jac, hlv, x0, None, None, 3, L.LFPSQPParams(maxiter=2))[3])
