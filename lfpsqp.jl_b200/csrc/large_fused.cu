@@ -1,9 +1,11 @@
-// large_fused.cu -- persistent, grid-synchronised projcg! (src/projcg.jl:71-112) for the large-n mode.
+// large_fused.cu -- persistent, grid-synchronised projcg! (src/projcg.jl:71-112) and pcg! (src/retractions.jl:179-246)
+// for the large-n mode, with the cross-GPU all-reduces of the column-sharded mode done inside the kernels.
 //
 // The unfused path (large.cu::projcg) spends 8 dependent launches per CG iteration (11 with the cross-GPU all-reduces);
 // at C5 that is ~25 us of launch/drain gaps on top of 334 us of HBM time, and at 8 GPUs (41 us of HBM time per
 // iteration) the gaps dominate.  Here ONE cooperative kernel (one CTA per SM, 512 threads) runs a whole chunk of
-// iterations; the data dependencies between the phases of an iteration are grid barriers (cooperative groups), the CG
+// iterations; the data dependencies between the phases of an iteration are grid barriers (cooperative launch, one
+// release-add / acquire-spin counter), the CG
 // scalars are re-reduced redundantly by every CTA from per-CTA partials in a fixed order (bitwise identical on every
 // CTA => control flow stays grid-uniform), and projcg's exits (negative curvature, rg <= 0, ||g|| < tol, iteration
 // cap) are taken on the device exactly as in the unfused kernels.
@@ -31,7 +33,6 @@ using namespace lfpsqp;
 namespace {
 
 constexpr int FT = 512;      // threads per CTA
-constexpr int FR = 8;        // rows per sweep of the row phase
 constexpr int TR = 16;       // rows per sweep of the triangular phases
 constexpr int CU = 16;       // 128-bit loads in flight per thread in the streaming phases
 constexpr int RCH = 2048;    // column pairs per shared-memory chunk of rp in the row phase (2 buffers x 32 KB)
@@ -52,7 +53,6 @@ struct FusedArgs {
   int rank, world;
   unsigned long long *epoch;
   unsigned *bar;             // grid-barrier arrival counter
-  int rows_mode;
 };
 
 // ---- in-kernel all-reduce over NVLink: push model with flag-in-data mailboxes (the "LL" idea: every 16-byte entry
@@ -522,8 +522,6 @@ int fused_projcg_chunk(LargeState &S, int iters, int first, double *xs, double *
   a.xs = xs; a.dc = dc; a.r = r; a.Ad = Ad; a.rp = rp; a.gp = gp; a.tm = S.tm; a.tu = S.tu;
   a.part = S.fused_part; a.lp_rg = S.lp + 3 * (size_t)MAXP; a.np_rg = S.np_loop; a.first = first; a.max_iters = iters;
   a.ctrl = S.ctrl;
-  static const int rows_mode = getenv("LFPSQP_FUSED_ROWS") ? atoi(getenv("LFPSQP_FUSED_ROWS")) : 0;
-  a.rows_mode = rows_mode;
   a.bar = reinterpret_cast<unsigned *>(S.fused_part + 3 * (size_t)S.fused_grid + 8);
   cudaMemsetAsync(a.bar, 0, sizeof(unsigned), S.stream);
   static const bool want_prof = getenv("LFPSQP_FUSED_PROF") != nullptr;
@@ -556,7 +554,7 @@ int fused_pcg(LargeState &S, double *dx, double *r, double *pv, double *z) {
   a.J = S.J; a.Ginv = nullptr; a.hd = nullptr;
   a.xs = dx; a.dc = pv; a.r = r; a.Ad = z; a.rp = nullptr; a.gp = nullptr; a.tm = S.tm; a.tu = S.tu;
   a.part = S.fused_part; a.lp_rg = S.lp + 5 * (size_t)MAXP; a.np_rg = S.np_loop_raw; a.first = 1; a.max_iters = 0;
-  a.ctrl = S.ctrl; a.prof = nullptr; a.rows_mode = 0;
+  a.ctrl = S.ctrl; a.prof = nullptr;
   a.bar = reinterpret_cast<unsigned *>(S.fused_part + 3 * (size_t)S.fused_grid + 8);
   cudaMemsetAsync(a.bar, 0, sizeof(unsigned), S.stream);
   const size_t smem = ((size_t)((S.m + 1) & ~1) + 2 * FT + 4 * RCH) * sizeof(double);

@@ -41,6 +41,31 @@ for (n, m, nr) in [(4096, 200, False), (1000, 130, False), (4096, 200, True)]:
             abs(obj[-1] - oobj[-1]) / abs(oobj[-1]), rel(lam, olam), status, "OK" if ok else "MISMATCH"), flush=True)
     dist.barrier()
 
+# ---- finite bounds (2n embedding) column-sharded: every rank passes its slice of xl, xu
+for (n, m, seed, nr) in [(256, 16, 2, False), (256, 16, 2, True), (512, 32, 1, True)]:
+    Q, A, b, xt, w, x0 = L.make_diagquad(n, m, seed=seed, cond=50.0)
+    rng = np.random.default_rng(seed + 10)
+    xl = x0 - rng.uniform(0.05, 1.0, n); xu = x0 + rng.uniform(0.05, 1.0, n)
+    col0, nloc = D.column_range(n, world, rank)
+    fam = L.families.Family(L.families.DIAGQUAD, "diagquad", n, m, 0, D.shard_diagquad(Q, A, b, xt, w, col0, nloc))
+    P = L.LargeProblem(fam, ctx, col0=col0, n_loc=nloc, n_global=n)
+    P.set_bounds(xl[col0:col0 + nloc], xu[col0:col0 + nloc])
+    x, obj, lam, info, st, status = P.solve(x0[col0:col0 + nloc], L.LFPSQPParams(do_project_retract=not nr), return_stats=True)
+    parts = [None] * world
+    dist.all_gather_object(parts, (col0, x))
+    if rank == 0:
+        from oracle import oracle as O
+        xfull = np.concatenate([p[1] for p in sorted(parts, key=lambda p: p[0])])
+        blob = np.concatenate([Q.ravel(), A.ravel(), b, xt, w])
+        op = O.default_params(do_project_retract=0 if nr else 1)
+        ox, oobj, olam, ot, ost = O.optimize("diagquad", n, m, 0, x0, xl=xl, xu=xu, fam_params=blob, params=op)
+        with O.variant("fma"):
+            fx = O.optimize("diagquad", n, m, 0, x0, xl=xl, xu=xu, fam_params=blob, params=op)[0]
+        print("world=%d BOUNDS n=%d m=%d nr=%s: gpu %s %d orc %d %d  x err %.2e (oracle-fma %.2e) f err %.2e status %d" % (
+            world, n, m, nr, info.condition.name, info.iter, ot["condition"], ot["iter"], rel(xfull, ox), rel(fx, ox),
+            abs(obj[-1] - oobj[-1]) / abs(oobj[-1]), status), flush=True)
+    dist.barrier()
+
 if "c5" in sys.argv:
     n, m, K = 65536, 2048, 64
     col0, nloc = D.column_range(n, world, rank)
