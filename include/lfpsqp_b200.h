@@ -147,7 +147,11 @@ int lfpsqp_solve_batched_dev(lfpsqp_ctx *ctx, int family, int64_t n, int64_t m, 
 /*
  * Large-n mode: ONE instance with a dense m x n constraint Jacobian, host-orchestrated whole-GPU kernels
  * (FP64 DMMA Gram + blocked Cholesky replace ksvd!, src/la_helper.jl:8-34 / optimize.jl:291-293; streaming passes over
- * J replace kgemv!, la_helper.jl:36-44).  Families: LFPSQP_FAM_DIAGQUAD, LFPSQP_FAM_THOMSON.  No finite bounds yet.
+ * J replace kgemv!, la_helper.jl:36-44).  Families: LFPSQP_FAM_DIAGQUAD, LFPSQP_FAM_THOMSON,
+ * LFPSQP_FAM_HOST (params = const lfpsqp_host_callbacks*).  Finite bounds xl <= x <= xu run the reference's 2n-variable
+ * embedding (src/inequality_helper.jl): lfpsqp_large_set_bounds after lfpsqp_large_setup, or the xl/xu arguments of
+ * lfpsqp_solve_large / lfpsqp_solve_host.  projcg! on diagonal Lagrangian Hessians and pcg! run as persistent cooperative
+ * kernels (large_fused.cu); LFPSQP_FUSED_PROJCG=0 in the environment selects the launch-per-phase loops.
  * Column sharding: with a communicator (lfpsqp_comm_init) rank g owns columns [col0, col0+n_loc) of J and the same
  * entries of every n-vector; m-vectors and the m x m factor are replicated; only the Gram, the m-vector J v and the
  * CG scalars are all-reduced.  Without a communicator col0 = 0, n_loc = n.

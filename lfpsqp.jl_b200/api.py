@@ -64,7 +64,9 @@ class LFPSQPParams:
 
     def to_c(self):
         if self.callback is not None:
-            raise _lib.LFPSQPError("param.callback (optimize.jl:432-434) is not supported on the device path")
+            raise _lib.LFPSQPError("param.callback (optimize.jl:432-434) needs the host-callback form "
+                                    "optimize(f, grad!, c!, jac!, hess_lag_vec!, x0, xl, xu, m, param); registered device "
+                                    "families run whole solves on the GPU without returning to the host")
         p = _lib.CParams()
         for name, _ in _lib.CParams._fields_:
             if name == "_pad":
