@@ -6,7 +6,7 @@
 module LFPSQPB200
 import Random
 
-export optimize, optimize_batched, LFPSQPParams, TerminationInfo, DeviceFamily, rosenbrock, readme_equality,
+export optimize, optimize_batched, optimize_large, LFPSQPParams, TerminationInfo, DeviceFamily, rosenbrock, readme_equality,
        readme_inequality, thomson, diagquad
 
 const lib = joinpath(@__DIR__, "..", "liblfpsqp_b200.so")
@@ -138,5 +138,27 @@ function optimize(f, grad!, c!, jac!, hess_lag_vec!, x0::Vector{Float64}, xl, xu
     t.iter == param.maxiter && @warn "Maximum # of outer iterations reached"                      # optimize.jl:438-440
     x, obj[1:len[]], λ[1:m], TerminationInfo(TerminationCondition(t.condition), t.f_diff, t.step_diff, t.kkt_diff, t.iter)
 end
+
+# One large dense instance of a registered family on one GPU (large-n engine: DMMA Gram + Cholesky, streaming passes over J,
+# persistent fused projcg / pcg kernels, 2n bound embedding when xl / xu are finite): lfpsqp_solve_large.
+function optimize_large(fam::DeviceFamily, x0::Vector{Float64}, xl, xu, param::LFPSQPParams=LFPSQPParams())
+    n = length(x0); m = fam.m
+    H = param.maxiter + 1
+    x = Vector{Float64}(undef, n); obj = Vector{Float64}(undef, H); len = Ref{Int64}(0)
+    λ = Vector{Float64}(undef, max(m, 1)); term = Ref{CTerm}()
+    D = Ptr{Float64}
+    pl = isnothing(xl) ? D(C_NULL) : pointer(xl); pu = isnothing(xu) ? D(C_NULL) : pointer(xu)
+    rc = GC.@preserve fam x0 xl xu x obj λ ccall((:lfpsqp_solve_large, lib), Cint,
+            (Ptr{Cvoid}, Cint, Int64, Int64, D, D, D, D, Ref{LFPSQPParams}, D, D, Int64, Ref{Int64}, D, Ref{CTerm}, Ptr{Cvoid}),
+            context(), fam.id, n, m, fam.params, x0, pl, pu, param, x, obj, H, len, λ, term, C_NULL)
+    check(rc)
+    t = term[]
+    x, obj[1:len[]], λ[1:m], TerminationInfo(TerminationCondition(t.condition), t.f_diff, t.step_diff, t.kkt_diff, t.iter)
+end
+
+# Grafting into LFPSQP.jl itself is one method: every convenience method of src/optimize.jl:13-114 ends in the core at :119, so
+#     LFPSQP.optimize(f, grad!, c!, jac!, hess_lag_vec!, x0::Vector{Float64}, xl, xu, m::Int64, param::LFPSQP.LFPSQPParams) =
+#         LFPSQPB200.optimize(f, grad!, c!, jac!, hess_lag_vec!, x0, xl, xu, m, LFPSQPB200.LFPSQPParams(param); callback=param.callback)
+# (with a field-by-field LFPSQPParams converter) sends the whole driver to the GPU while the AD generators stay untouched.
 
 end # module
