@@ -65,3 +65,21 @@ def test_method_shapes_resolve():
         api._parse((fam.f, 1, 2))
     with pytest.raises(TypeError):
         api._family_of(lambda x: 0.0, None, None)
+
+
+def test_header_is_plain_c(tmp_path):
+    # the boundary is a C ABI: the header must compile as C99 (what a cgo / ccall / ctypes binder assumes), no C++-isms
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "lfpsqp_b200.h"\n'
+                   'int probe(lfpsqp_ctx *c, const lfpsqp_host_callbacks *cb, lfpsqp_params *p) {\n'
+                   '  lfpsqp_default_params(p);\n'
+                   '  return (int)sizeof(lfpsqp_term) + (int)sizeof(lfpsqp_stats) + (cb && c ? LFPSQP_FAM_HOST : LFPSQP_OK);\n'
+                   '}\n')
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only",
+                        "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
