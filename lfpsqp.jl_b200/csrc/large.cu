@@ -1036,7 +1036,7 @@ extern "C" int lfpsqp_large_set_bounds(lfpsqp_ctx *c, const double *xl_loc, cons
   }
   S.ineq = ineq != 0;
   S.nv = S.ineq ? 2 * nl : nl;
-  if (!S.ineq) { S.I = lfpsqp::IneqDev(); return LFPSQP_OK; }
+  if (!S.ineq) return LFPSQP_OK;   // S.I keeps its workspaces: bounds may be switched on again later
   if (!S.bq) {
     bool ok = true;
     double **nvv[] = {&S.bq, &S.br, &S.bs, &S.bt, &S.I.Dx, &S.I.Dy, &S.I.S, &S.I.lamy, &S.cvh, &S.pb};

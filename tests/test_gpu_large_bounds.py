@@ -87,6 +87,13 @@ def test_bounds_all_infinite_is_unbounded_path(L):
     P.set_bounds(-np.inf * np.ones(n), np.inf * np.ones(n))
     b2 = P.solve(x0)
     assert np.array_equal(a[0], b2[0]) and a[3] == b2[3]
+    # bounds can be switched on, off and on again on the same bound problem (workspaces are kept)
+    xl, xu = bounds_for(x0, 12, "box")
+    P.set_bounds(xl, xu); c1 = P.solve(x0)
+    P.set_bounds(None, None); c2 = P.solve(x0)
+    P.set_bounds(xl, xu); c3 = P.solve(x0)
+    assert np.array_equal(c2[0], a[0]) and np.array_equal(c1[0], c3[0]) and not np.array_equal(c1[0], a[0])
+    assert np.all(c1[0] >= xl - 2e-5) and np.all(c1[0] <= xu + 2e-5)
 
 
 def test_bounds_errors(L):
