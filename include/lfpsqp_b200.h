@@ -187,6 +187,14 @@ int lfpsqp_large_project(lfpsqp_ctx *ctx, const double *v_loc, double *v_out_loc
 int lfpsqp_large_projcg(lfpsqp_ctx *ctx, const double *x_loc, const double *lam, double tol, int64_t maxit, int chunk,
                         double *sol_out_loc, int64_t *iters, double *nr, int *status, double *ms);
 
+/*   projcg_general : projcg!(x, lambda, A, U, b, c; tol, maxit) (src/projcg.jl:40-121) in its general form (c != 0: x0 = U c, :55;
+ *             test/test_cg.jl:10-28): A = the family's Lagrangian Hessian at (x, lam), U = the orthonormal Cholesky-QR basis
+ *             J(x)' L^-T of range(J') (the reference's U up to an orthogonal change of basis), b (n_loc) and c (m) from the
+ *             caller; lambda_out = U'(b - A sol) (:115-118; NaN after a negative-curvature exit).  Needs factor at x first. */
+int lfpsqp_large_projcg_general(lfpsqp_ctx *ctx, const double *x_loc, const double *lam, const double *b_loc, const double *cvec,
+                                double tol, int64_t maxit, double *sol_out_loc, double *lambda_out, int64_t *iters, double *nr,
+                                int *status);
+
 /*   retract : retract!(cval, xnew, c!, xtilde, x, method) (src/retractions.jl:75-177 NR [method 0] / :265-441 ProjPenalty
  *             [method 1]) with the factorisation at x_base, as armijo! calls it (src/linesearch.jl:52); flag as the reference
  *   pcg     : pcg!(mu, J, no_precondition, x=0, r=b, ...) (src/retractions.jl:179-246) with J = jac(x_point) */
@@ -212,6 +220,22 @@ int lfpsqp_large_phase_ms(lfpsqp_ctx *ctx, double *out4);
  *                                       in [xaug | d (2n)]                out [d_proj (2n) | lambda (m) | lambda_y (n)] */
 int lfpsqp_ineq_op(lfpsqp_ctx *ctx, int op, int64_t n, int64_t m, const double *xl, const double *xu, const double *J,
                    const double *in, int64_t in_len, double *out, int64_t out_len);
+
+/* Unit-level line search: armijo! (which = 0, src/linesearch.jl:32-89) / exact_linesearch! (which = 1, :107-339) on ONE
+ * instance, called as the driver calls them (src/optimize.jl:396-420): g = grad f(x), fval = f(x), factorisation at x,
+ * retraction by the driver's rule (m > 0: NR iff !do_project_retract else ProjPenalty; m = 0: YRetract with finite
+ * bounds, else Euclidean).  x, d, xnew_out have the working length N (n, or 2n = [x | y] with finite bounds).
+ * out6 = [newf, f_diff, step_diff, alpha, tot_iter1, tot_iter2] = the reference's return tuple after the flag.
+ * Families: LFPSQP_FAM_BOXQUAD, LFPSQP_FAM_SIN.  Reference goldens: test/test_linesearch.jl:14-22 (alpha = 0.25), :24-32. */
+int lfpsqp_linesearch(lfpsqp_ctx *ctx, int which, int family, int64_t n, int64_t m, const double *fam_params, const double *x,
+                      const double *d, const double *xl, const double *xu, const lfpsqp_params *params, double *xnew_out,
+                      double *out6, int *flag);
+/* Unit-level augmented_hess_lag_vec! (src/inequality_helper.jl:144-158; test/test_inequalities.jl:157-177):
+ * dest = [H(x, lam) src_x + 2 lam_y.q.src_x ; 2 lam_y.s.src_y] with H the family's hess_lag_vec! at xaug[1:n].
+ * xaug, src, dest: 2n; lam: m; lamy: n.  Families: LFPSQP_FAM_BOXQUAD, LFPSQP_FAM_SIN. */
+int lfpsqp_aug_hess_vec(lfpsqp_ctx *ctx, int family, int64_t n, int64_t m, const double *fam_params, const double *xl,
+                        const double *xu, const double *xaug, const double *lam, const double *lamy, const double *src,
+                        double *dest);
 
 /* Communicator of the column-sharded large-n mode: one process per GPU, NCCL (bound with dlopen so the process shares
  * the libnccl.so.2 that e.g. torch.distributed loaded; nccl_lib_path may be NULL).  Rank 0 creates the 128-byte unique

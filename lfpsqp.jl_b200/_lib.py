@@ -33,7 +33,7 @@ EXPORTS = [
     "lfpsqp_large_solve", "lfpsqp_large_factor", "lfpsqp_large_project", "lfpsqp_large_projcg",
     "lfpsqp_comm_unique_id", "lfpsqp_comm_init", "lfpsqp_comm_destroy", "lfpsqp_large_retract", "lfpsqp_large_pcg",
     "lfpsqp_ineq_op", "lfpsqp_large_phase_ms", "lfpsqp_comm_ipc_export", "lfpsqp_comm_ipc_import", "lfpsqp_comm_mode",
-    "lfpsqp_large_set_bounds", "lfpsqp_solve_host",
+    "lfpsqp_large_set_bounds", "lfpsqp_solve_host", "lfpsqp_linesearch", "lfpsqp_aug_hess_vec", "lfpsqp_large_projcg_general",
 ]
 
 _lib = None
@@ -81,6 +81,9 @@ def load():
         lib.lfpsqp_comm_mode.argtypes = [P]
         lib.lfpsqp_large_set_bounds.argtypes = [P, P, P]
         lib.lfpsqp_solve_host.argtypes = [P, P, I, I, P, P, P, P, P, P, I, P, P, P, P]
+        lib.lfpsqp_linesearch.argtypes = [P, C.c_int, C.c_int, I, I, P, P, P, P, P, P, P, P, P]
+        lib.lfpsqp_aug_hess_vec.argtypes = [P, C.c_int, I, I, P, P, P, P, P, P, P, P]
+        lib.lfpsqp_large_projcg_general.argtypes = [P, P, P, P, P, C.c_double, I, P, P, P, P, P]
         _lib = lib
     return _lib
 

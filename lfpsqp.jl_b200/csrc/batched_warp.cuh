@@ -57,6 +57,8 @@ struct Solver {
   int status;
   int rank;      // numerical rank of the (projected) Jacobian, optimize.jl:297-302
   bool pinv;     // Gm holds the truncated pseudo-inverse G^+ instead of the Cholesky factor
+  double ls_alpha;        // step length returned by the last armijo! / exact_linesearch! (linesearch.jl:88, :338)
+  int ls_it1, ls_it2;     // tot_iter1 / tot_iter2 of the last line search
 
   double *x, *xnew, *xtil, *gr, *d, *nd, *w0, *w1, *w2, *w3, *w4, *J, *Gm, *cval, *lam, *tm, *cvaug, *ub, *scr, *Dx, *Dy,
       *S, *lamy, *Dnr, *nrt;
@@ -605,11 +607,13 @@ struct Solver {
     double f_diff = INFINITY, step_diff = INFINITY, alpha = prm.alpha, newf = 0.0;
     int flag = 0;
     double ar_dot = dot(d, gr, N);
+    ls_it1 = ls_it2 = 0;
     while (step_diff > prm.eps_x) {
       for (int k = g.lane; k < N; k += G::SIZE) xtil[k] = x[k] + alpha * d[k];
       g.sync();
       int i1, i2;
       flag = retract(kind, &i1, &i2);
+      ls_it1 += i1; ls_it2 += i2;
       st.armijo_trials++;
       // linesearch.jl:57-60 has no lower bound on alpha in this branch: when the retraction fails at EVERY alpha the
       // reference spins forever once alpha has underflowed to 0.  Stop at the floor the other branch uses (:82-85):
@@ -626,6 +630,7 @@ struct Solver {
       if (alpha < 1e-100) { flag = 99; break; }                           // :82-85
     }
     *newf_o = newf; *f_diff_o = f_diff; *step_diff_o = step_diff;
+    ls_alpha = alpha;
     return flag;
   }
 
@@ -643,9 +648,11 @@ struct Solver {
       for (int k = g.lane; k < N; k += G::SIZE) xtil[k] = x[k] + al * d[k];
       g.sync();
       flag = retract(kind, &i1, &i2);
+      ls_it1 += i1; ls_it2 += i2;
       st.armijo_trials++;
       copy(pt, xnew, N);
     };
+    ls_it1 = ls_it2 = 0;
     copy(x_d, x, N); f_d = fval;
     while (true) {                                             // growing (:150-189)
       swp = x_b; x_b = x_c; x_c = x_d; x_d = swp;
@@ -694,7 +701,7 @@ struct Solver {
     }
     (void)f_a; (void)f_d;
     double newf;
-    if (f_b < f_c) { copy(xnew, x_b, N); newf = f_b; } else { copy(xnew, x_c, N); newf = f_c; }   // (:325-333)
+    if (f_b < f_c) { copy(xnew, x_b, N); newf = f_b; ls_alpha = a_b; } else { copy(xnew, x_c, N); newf = f_c; ls_alpha = a_c; }   // (:325-333)
     double s = 0;
     for (int k = g.lane; k < NA; k += G::SIZE) { double t = xnew[k] - x[k]; s += t * t; }
     *step_diff_o = sqrt(g.sum(s));

@@ -50,6 +50,7 @@ static void finalize(LargeState &S, unsigned summask, unsigned maxmask, unsigned
 static int read_ctrl(lfpsqp_ctx *c, LargeState &S) {
   CK(cudaMemcpyAsync(S.hctrl, S.ctrl, sizeof(LargeCtrl), cudaMemcpyDeviceToHost, S.stream));
   CK(cudaStreamSynchronize(S.stream));
+  CK(cudaGetLastError());   // a refused launch (bad configuration) since the last check must not pass silently
   return 0;
 }
 static void write_ctrl_fields(LargeState &S) {  // push the host copy (tolerances, limits, statuses) to the device
@@ -374,12 +375,26 @@ static void project(LargeState &S, double *v, double *lam_out, int pred, int wan
 
 // ------------------------------------------------------------------ projcg! (projcg.jl:40-121), c = 0
 // b = S.d (projected -grad). Solution -> S.nd. Fills S.hctrl (status/iter/nr) on return.
-static int projcg(lfpsqp_ctx *c, LargeState &S, double tol, int64_t maxit, int chunk) {
+// cvec (device, m doubles, replicated) selects the general form of projcg.jl:55: x0 = U c, r = A x0 - b, with U the
+// Cholesky-QR basis J' L^-T (orthonormal columns spanning the same space as the reference's U); the
+// driver always passes c = 0 (cvec = nullptr).  lam_out receives U'(b - A x) (projcg.jl:115-118).
+static int projcg(lfpsqp_ctx *c, LargeState &S, double tol, int64_t maxit, int chunk, const double *cvec = nullptr,
+                  double *lam_out = nullptr) {
   const int64_t n = S.nv;   // working length: n_loc, or 2 n_loc with bounds
   const int ns = S.m > 0 ? S.nsplit : 0;
   double *xs = S.nd, *r = S.w0, *dc = S.w1, *Ad = S.w2, *rp = S.w3, *gp = S.w4;
   const double *b = S.d;
   if (S.family == LFPSQP_FAM_HOST) chunk = 1;   // the Hessian callback runs on the host: one status check per iteration
+  if (cvec && S.m > 0 && !S.ineq) {
+    const int m = S.m;
+    tri_gemv_kernel<<<(m + 7) / 8, 256, m * sizeof(double), S.stream>>>(S.XT, S.ldm, m, cvec, S.tu, 1, nullptr, S.ctrl, 0);   // L^-T c
+    cols_dot(S, S.J, S.ldj, m, S.n_loc, S.tu, 0);
+    const double *cp = S.cpart; const int64_t nl = S.n_loc;
+    vec(S, n, [=] __device__(int64_t j, double *) { double s = 0.0; for (int k = 0; k < ns; k++) s += cp[(int64_t)k * nl + j]; xs[j] = s; });
+    hess_apply(S, r, xs, 0);
+    vec(S, n, [=] __device__(int64_t i, double *) { r[i] -= b[i]; });
+    S.launches += 3;
+  } else
   vec(S, n, [=] __device__(int64_t i, double *) { xs[i] = 0.0; r[i] = -b[i]; });
   // g = r - U U' r (projcg.jl:59-60) ; r = g ; d = -g ; rg partials -> loop slot 3 (= 2 + (par^1) for k = 0)
   proj_passes(S, r, nullptr, 0);
@@ -394,7 +409,7 @@ static int projcg(lfpsqp_ctx *c, LargeState &S, double tol, int64_t maxit, int c
   write_ctrl_fields(S);
   int64_t k = 0;
   // persistent fused path (large_fused.cu): one cooperative kernel per chunk instead of 8 launches per iteration
-  bool fused = S.fused_ok && lim > 0;
+  bool fused = S.fused_ok && lim > 0 && !cvec;
   while (fused && S.hctrl->status == 0) {
     if (fused_projcg_chunk(S, std::max(4 * chunk, 64), k == 0, xs, r, dc, Ad, rp, gp)) {
       if (k == 0) { fused = false; break; }          // not eligible / launch refused before anything ran: unfused path
@@ -427,6 +442,20 @@ static int projcg(lfpsqp_ctx *c, LargeState &S, double tol, int64_t maxit, int c
     vec(S, n, [=] __device__(int64_t i, double *) { xs[i] = dc[i] / sqrt(ctrl->s[0]); });
     S.launches += 2;
     S.hctrl->nr = INFINITY;
+  }
+  if (lam_out && S.m > 0 && !S.ineq) {   // lambda = U'(b - A x) (projcg.jl:115-118) = L^-1 J (b - A x); NaN after a negative-curvature exit (:80)
+    if (S.hctrl->status == 2) {
+      vec(S, S.m, [=] __device__(int64_t a, double *) { lam_out[a] = NAN; });
+    } else {
+      const int st_keep = S.hctrl->status;
+      hess_apply(S, Ad, xs, 0);
+      vec(S, n, [=] __device__(int64_t i, double *) { Ad[i] = b[i] - Ad[i]; });
+      rows_dot(S, S.J, S.ldj, S.m, S.n_loc, Ad, S.tm, 0);
+      if (S.world > 1) comm_allreduce(S, S.tm, S.m);
+      tri_gemv_kernel<<<(S.m + 7) / 8, 256, S.m * sizeof(double), S.stream>>>(S.Linv, S.ldm, S.m, S.tm, lam_out, 0, nullptr, S.ctrl, 0);
+      S.launches += 2;
+      (void)st_keep;
+    }
   }
   return 0;
 }
@@ -969,6 +998,9 @@ extern "C" int lfpsqp_large_setup(lfpsqp_ctx *c, int family, int64_t n_global, i
   cudaFuncSetAttribute(dgemm_nt_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgemm_smem_bytes<128>());
   cudaFuncSetAttribute(dgemm_nt_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgemm_smem_bytes<64>());
   cudaFuncSetAttribute(potf2_inv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 64 * 65 * sizeof(double)));
+  // the staged m-vector of tri_gemv / the row-split of cols_dot exceed the 48 KB default for m > 6144
+  CK(cudaFuncSetAttribute(tri_gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(mm * sizeof(double), 1024)));
+  CK(cudaFuncSetAttribute(cols_dot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(mm * sizeof(double), 1024)));
   CK(cudaStreamSynchronize(S.stream));
   {
     const char *env = getenv("LFPSQP_FUSED_PROJCG");   // "0" selects the multi-kernel projcg loop (A/B measurements, tests)
@@ -1147,6 +1179,36 @@ extern "C" int lfpsqp_large_projcg(lfpsqp_ctx *c, const double *x_loc, const dou
   if (nr) *nr = S.hctrl->nr;
   if (status) *status = S.hctrl->status;
   c->last_ms = t; c->last_launches = S.launches;
+  return LFPSQP_OK;
+}
+
+// Unit-level: the general projcg!(x, lambda, A, U, b, c; tol, maxit) of src/projcg.jl:40-121 (test/test_cg.jl:10-28 uses c != 0):
+// A = Lagrangian Hessian of the family at (x_point, lam), U = orthonormal Cholesky-QR basis J(x_point)' L^-T of the range of
+// J', b (n_loc) and c (m) given by the caller.  Needs lfpsqp_large_factor at x_point first.  Runs the launch-per-phase loop.
+extern "C" int lfpsqp_large_projcg_general(lfpsqp_ctx *c, const double *x_loc, const double *lam, const double *b_loc,
+                                           const double *cvec, double tol, int64_t maxit, double *sol_out_loc,
+                                           double *lambda_out, int64_t *iters, double *nr, int *status) {
+  int rc = need_large(c); if (rc) return rc;
+  LargeState &S = *c->large;
+  if (S.ineq) return c->fail(LFPSQP_ERR_UNSUPPORTED, "unit-level large-n ops work on the unbounded problem (lfpsqp_ineq_op covers the bound operators)");
+  if (!x_loc || !b_loc) return c->fail(LFPSQP_ERR_ARG, "x and b are required");
+  const int64_t n = S.n_loc;
+  CK(cudaMemcpyAsync(S.x, x_loc, n * 8, cudaMemcpyHostToDevice, S.stream));
+  CK(cudaMemcpyAsync(S.d, b_loc, n * 8, cudaMemcpyHostToDevice, S.stream));
+  if (S.m > 0) { if (lam) CK(cudaMemcpyAsync(S.lam, lam, S.m * 8, cudaMemcpyHostToDevice, S.stream)); else cudaMemsetAsync(S.lam, 0, S.m * 8, S.stream); }
+  if (S.m > 0 && cvec) CK(cudaMemcpyAsync(S.nr_t1, cvec, S.m * 8, cudaMemcpyHostToDevice, S.stream));
+  memset(S.hctrl, 0, sizeof(LargeCtrl)); write_ctrl_fields(S);
+  fam_hess_prepare(S, S.x, S.lam);
+  S.reset_counters();
+  if (projcg(c, S, tol, maxit, S.cg_chunk, (S.m > 0 && cvec) ? S.nr_t1 : nullptr, (S.m > 0 && lambda_out) ? S.nr_t2 : nullptr)) return LFPSQP_ERR_CUDA;
+  const int st = S.hctrl->status; const int64_t it = S.hctrl->iter; const double nrv = S.hctrl->nr;
+  if (sol_out_loc) CK(cudaMemcpyAsync(sol_out_loc, S.nd, n * 8, cudaMemcpyDeviceToHost, S.stream));
+  if (lambda_out && S.m > 0) CK(cudaMemcpyAsync(lambda_out, S.nr_t2, S.m * 8, cudaMemcpyDeviceToHost, S.stream));
+  CK(cudaStreamSynchronize(S.stream));
+  if (iters) *iters = it;
+  if (nr) *nr = nrv;
+  if (status) *status = st;
+  c->last_launches = S.launches;
   return LFPSQP_OK;
 }
 

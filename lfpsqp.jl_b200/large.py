@@ -91,6 +91,18 @@ class LargeProblem:
                                                      C.cast(C.pointer(fl), C.c_void_p), C.cast(C.pointer(it), C.c_void_p)))
         return x, r, fl.value, it.value
 
+    def projcg_general(self, x, lam, b, c, tol=1e-6, maxit=10000):
+        """projcg!(x, lambda, A, U, b, c) (src/projcg.jl:40-121) with c != 0; needs factor(x) first.
+        -> dict(sol, lam, iters, nr, status)"""
+        f64 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        x, lam, b, c = map(f64, (x, lam, b, c))
+        sol = np.empty(self.n_loc); lout = np.zeros(max(self.m, 1))
+        it = C.c_int64(0); nr = C.c_double(0); st = C.c_int(0)
+        self.ctx.check(self.ctx.lib.lfpsqp_large_projcg_general(self.ctx.h, _lib.ptr(x), _lib.ptr(lam), _lib.ptr(b), _lib.ptr(c), tol, maxit,
+                                                                _lib.ptr(sol), _lib.ptr(lout), C.cast(C.pointer(it), C.c_void_p),
+                                                                C.cast(C.pointer(nr), C.c_void_p), C.cast(C.pointer(st), C.c_void_p)))
+        return dict(sol=sol, lam=lout[:self.m], iters=it.value, nr=nr.value, status=st.value)
+
     def projcg(self, x, lam=None, tol=0.0, maxit=10, chunk=0, want_solution=True):
         x = np.ascontiguousarray(x, dtype=np.float64)
         lam = None if lam is None else np.ascontiguousarray(lam, dtype=np.float64)
@@ -100,6 +112,35 @@ class LargeProblem:
                                                         C.cast(C.pointer(it), C.c_void_p), C.cast(C.pointer(nr), C.c_void_p),
                                                         C.cast(C.pointer(st), C.c_void_p), C.cast(C.pointer(ms), C.c_void_p)))
         return dict(sol=sol, iters=it.value, nr=nr.value, status=st.value, ms=ms.value)
+
+
+def linesearch(which, fam, x, d, xl=None, xu=None, param=None, ctx=None):
+    """armijo! / exact_linesearch! (src/linesearch.jl:32-89, :107-339) on one instance, as the driver calls them.
+    which: "armijo" | "exact".  x, d: working length (n, or 2n = [x | y] with finite bounds).
+    -> (flag, tot_iter1, tot_iter2, newf, f_diff, step_diff, alpha, xnew): the reference's return tuple + xnew."""
+    ctx = ctx or _lib.default_context()
+    cp = (param or LFPSQPParams()).to_c()
+    x = np.ascontiguousarray(x, dtype=np.float64); d = np.ascontiguousarray(d, dtype=np.float64)
+    xl = None if xl is None else np.ascontiguousarray(xl, dtype=np.float64)
+    xu = None if xu is None else np.ascontiguousarray(xu, dtype=np.float64)
+    fp = np.ascontiguousarray(fam.params, dtype=np.float64).ravel()
+    xnew = np.empty_like(x); out6 = np.zeros(6); fl = C.c_int(0)
+    ctx.check(ctx.lib.lfpsqp_linesearch(ctx.h, 0 if which == "armijo" else 1, fam.id, fam.n, fam.m, _lib.ptr(fp), _lib.ptr(x),
+                                        _lib.ptr(d), _lib.ptr(xl), _lib.ptr(xu), C.cast(C.pointer(cp), C.c_void_p), _lib.ptr(xnew),
+                                        _lib.ptr(out6), C.cast(C.pointer(fl), C.c_void_p)))
+    return fl.value, int(out6[4]), int(out6[5]), out6[0], out6[1], out6[2], out6[3], xnew
+
+
+def aug_hess_vec(fam, xl, xu, xaug, lam, lamy, src, ctx=None):
+    """augmented_hess_lag_vec! (src/inequality_helper.jl:144-158) on the device: -> dest (2n)."""
+    ctx = ctx or _lib.default_context()
+    f64 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+    xl, xu, xaug, lam, lamy, src = map(f64, (xl, xu, xaug, lam, lamy, src))
+    fp = np.ascontiguousarray(fam.params, dtype=np.float64).ravel()
+    dest = np.zeros(2 * fam.n)
+    ctx.check(ctx.lib.lfpsqp_aug_hess_vec(ctx.h, fam.id, fam.n, fam.m, _lib.ptr(fp), _lib.ptr(xl), _lib.ptr(xu), _lib.ptr(xaug),
+                                          _lib.ptr(lam), _lib.ptr(lamy), _lib.ptr(src), _lib.ptr(dest)))
+    return dest
 
 
 def ineq_op(op, xl, xu, inp, J=None, ctx=None):

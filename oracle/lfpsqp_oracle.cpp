@@ -72,6 +72,11 @@ static void ksvd(double *A, int M, int N, double *U, double *S, double *VT, SvdW
 
 /* ------------------------------------------------------------------ small BLAS-like helpers (counted) */
 static inline double dot(const double *a, const double *b, int64_t n) {
+#ifdef ORC_SEQ_SUM
+  /* rounding-sensitivity probe (Makefile: liblfpsqp_oracle_seq.so): plain left-to-right summation, as Julia's generic
+     fallback would do; the reference does not pin the summation order (BLAS ddot) */
+  { double s = 0; for (int64_t i = 0; i < n; i++) s += a[i] * b[i]; g_flops += 2.0 * n; return s; }
+#endif
   /* four partial sums, as an optimised BLAS ddot would keep (summation order is not pinned by the reference) */
   double s0 = 0, s1 = 0, s2 = 0, s3 = 0; int64_t i = 0;
   for (; i + 4 <= n; i += 4) { s0 += a[i] * b[i]; s1 += a[i+1] * b[i+1]; s2 += a[i+2] * b[i+2]; s3 += a[i+3] * b[i+3]; }
@@ -98,6 +103,10 @@ static void gemv(char t, int64_t M, int64_t N, double alpha, const double *A, in
     }
   } else {
     for (int64_t j = 0; j < N; j++) {
+#ifdef ORC_SEQ_SUM
+      { const double *cj = A + j * lda; double s = 0; for (int64_t i = 0; i < M; i++) s += cj[i] * x[i];
+        y[j] = alpha * s + ((beta == 0.0) ? 0.0 : beta * y[j]); continue; }
+#endif
       const double *col = A + j * lda; double s0 = 0, s1 = 0, s2 = 0, s3 = 0; int64_t i = 0;
       for (; i + 4 <= M; i += 4) { s0 += col[i] * x[i]; s1 += col[i+1] * x[i+1]; s2 += col[i+2] * x[i+2]; s3 += col[i+3] * x[i+3]; }
       for (; i < M; i++) s0 += col[i] * x[i];

@@ -107,3 +107,92 @@ def test_retractions_match_reference_test(L, oracle, method):
             assert abs(step @ (xnew - xt)) < 1e-6
         else:
             assert np.linalg.norm(step) >= np.linalg.norm(xnew - x0) - tol
+
+
+def test_linesearch_reference_goldens_on_device(L, oracle):
+    # test/test_linesearch.jl:14-22 (armijo!: f = x^2, x = -0.23, d = 1 -> alpha = step_diff = 0.25 exactly) and :24-32
+    # (exact_linesearch!: alpha ~= 0.23, atol 1e-6) run on the DEVICE through lfpsqp_linesearch; boxquad with t = 0 is f = |x|^2
+    fam = L.families.boxquad(np.zeros(1))
+    x = np.array([-0.23]); d = np.array([1.0])
+    flag, it1, it2, newf, f_diff, step_diff, alpha, xnew = L.linesearch("armijo", fam, x, d)
+    assert flag == it1 == it2 == 0
+    assert x[0] == -0.23                                   # input not changed
+    assert newf == pytest.approx(xnew[0] ** 2, rel=1e-15) and f_diff == pytest.approx(0.23 ** 2 - newf, rel=1e-14)
+    assert alpha == 0.25 and step_diff == pytest.approx(0.25, rel=1e-15)
+    oflag, oxnew, onewf, ofd, osd, oal = oracle.linesearch_euclid("boxquad", 1, x, d, "armijo", fam_params=np.zeros(3))
+    assert (flag, alpha) == (oflag, oal) and xnew[0] == oxnew[0] and newf == onewf
+    flag, it1, it2, newf, f_diff, step_diff, alpha, xnew = L.linesearch("exact", fam, x, d)
+    assert flag == it1 == it2 == 0
+    assert newf == pytest.approx(xnew[0] ** 2, rel=1e-15) and f_diff == pytest.approx(0.23 ** 2 - newf, rel=1e-12)
+    assert step_diff == pytest.approx(alpha, rel=1e-12) and abs(alpha - 0.23) < 1e-6
+    oflag, oxnew, onewf, ofd, osd, oal = oracle.linesearch_euclid("boxquad", 1, x, d, "exact", fam_params=np.zeros(3))
+    assert flag == oflag and alpha == pytest.approx(oal, rel=1e-12) and xnew[0] == pytest.approx(oxnew[0], rel=1e-12)
+    # with retraction: the sin system (test/test_retractions.jl:34-54), NR and ProjPenalty, tangent direction
+    rng = np.random.default_rng(12)
+    n, m = 24, 6
+    t = rng.standard_normal(n)
+    fam = L.families.sin_system(n, m, t)
+    x0 = np.zeros(n)                                       # feasible: x[2i] = sin(x[2i-1]) = 0
+    J = np.zeros((m, n))
+    for i in range(m):
+        J[i, 2 * i + 1] = 1.0; J[i, 2 * i] = -np.cos(x0[2 * i])
+    g = x0 - t
+    dd = -g - J.T @ np.linalg.solve(J @ J.T, J @ (-g))
+    for nr in (False, True):
+        prm = L.LFPSQPParams(do_project_retract=not nr)
+        flag, it1, it2, newf, f_diff, step_diff, alpha, xnew = L.linesearch("armijo", fam, x0, dd, param=prm)
+        cv = np.array([xnew[2 * i + 1] - np.sin(xnew[2 * i]) for i in range(m)])
+        assert flag == 0 and np.max(np.abs(cv)) < 1e-6 and it1 >= 1
+        assert newf == pytest.approx(0.5 * np.sum((xnew - t) ** 2), rel=1e-13)
+        assert newf - 0.5 * np.sum((x0 - t) ** 2) <= 1e-4 * alpha * (dd @ g)                 # Armijo-Goldstein (linesearch.jl:75)
+        assert step_diff == pytest.approx(np.linalg.norm(xnew - x0), rel=1e-12)
+        assert (it2 == 0) if nr else (it2 >= 1)
+
+
+def test_augmented_hessian_action_on_device(L):
+    # test/test_inequalities.jl:157-177: dest = bigH v, bigH = [H + 2 diag(lam_y.q), 0; 0, 2 diag(lam_y.s)], H = Lagrangian Hessian
+    rng = np.random.default_rng(9)
+    n, m = 16, 5
+    xl, xu, x = _ineq_setup(rng, n)
+    q, r, s, t, il, ip = __import__("oracle.oracle", fromlist=["x"]).ineq_data(xl, xu)
+    xaug = L.ineq_op("initial_y", xl, xu, x)
+    lam = rng.standard_normal(m); lamy = rng.standard_normal(n); v = rng.standard_normal(2 * n)
+    fam = L.families.sin_system(n, m, rng.standard_normal(n))
+    dest = L.aug_hess_vec(fam, xl, xu, xaug, lam, lamy, v)
+    H = np.eye(n)
+    for i in range(m):
+        H[2 * i, 2 * i] += lam[i] * np.sin(xaug[2 * i])
+    bigH = np.block([[H + 2 * np.diag(lamy * q), np.zeros((n, n))], [np.zeros((n, n)), 2 * np.diag(lamy * s)]])
+    assert np.allclose(dest, bigH @ v, rtol=0, atol=1e-14)
+    fam = L.families.boxquad(rng.standard_normal(n), a=np.ones(n), b=1.0)
+    dest = L.aug_hess_vec(fam, xl, xu, xaug, lam[:1], lamy, v)
+    bigH = np.block([[2 * np.eye(n) + 2 * np.diag(lamy * q), np.zeros((n, n))], [np.zeros((n, n)), 2 * np.diag(lamy * s)]])
+    assert np.allclose(dest, bigH @ v, rtol=0, atol=1e-14)
+
+
+def test_projcg_general_c_nonzero(L, oracle):
+    # test/test_cg.jl:5-28: projcg! with c != 0 (x0 = U c, projcg.jl:55): nr < tol, |U'x - c| small, KKT residual small
+    n, m = 1000, 10
+    Q, A, b, x0, fam, P = _diagquad(L, n, m, 8)
+    J = Q * x0[None, :] + A
+    P.factor(x0, want=())
+    rng = np.random.default_rng(8)
+    lam = 0.1 * rng.standard_normal(m)
+    w = fam.params[2 * m * n + m + n:]
+    hd = w + Q.T @ lam
+    assert np.all(hd > 0)
+    Lc = np.linalg.cholesky(J @ J.T)
+    U = J.T @ np.linalg.inv(Lc).T                              # orthonormal basis of range(J') (Cholesky-QR)
+    bv = rng.standard_normal(n); cv = rng.standard_normal(m)
+    bigM = np.block([[np.diag(hd), U], [U.T, np.zeros((m, m))]])
+    rhs = np.r_[bv, cv]
+    for tol in (1e-6, 1e-9, 1e-12):
+        r = P.projcg_general(x0, lam, bv, cv, tol=tol)
+        assert r["status"] in (1, 3) and r["nr"] < tol
+        assert np.linalg.norm(U.T @ r["sol"] - cv) < 1e-12
+        assert np.linalg.norm(bigM @ np.r_[r["sol"], r["lam"]] - rhs) < max(10 * tol, 1e-11)
+        ox, olam, oit, onr = oracle.projcg_dense(np.diag(hd), U, bv, cv, tol=tol)
+        assert abs(r["iters"] - oit) <= 1 and rel(r["sol"], ox) < 1e-8
+    # c = 0 through the same entry point equals the dedicated path's structure: U'x = 0
+    r = P.projcg_general(x0, lam, bv, np.zeros(m), tol=1e-10)
+    assert np.linalg.norm(U.T @ r["sol"]) < 1e-12
