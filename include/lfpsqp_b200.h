@@ -117,6 +117,12 @@ const char *lfpsqp_version(void);
 void lfpsqp_default_params(lfpsqp_params *p);                      /* src/LFPSQP.jl:57-81 */
 int lfpsqp_ctx_create(int device, lfpsqp_ctx **out);               /* fails loudly (LFPSQP_ERR_CUDA) without a GPU */
 void lfpsqp_ctx_destroy(lfpsqp_ctx *ctx);
+/* Multi-GPU context (SURVEY.md 8b "create context (device list)"): lfpsqp_solve_batched on such a ctx shards the B instances
+ * into contiguous, balanced ranges over the listed devices from ONE host call -- one host thread, one stream pipeline and one
+ * device arena per GPU, no collective (the instances are independent); results land in disjoint slices of the caller's
+ * arrays.  Every other entry point runs on devices[0].  Each device may be listed once.  destroy releases all of them. */
+int lfpsqp_ctx_create_multi(const int *devices, int ndev, lfpsqp_ctx **out);
+int lfpsqp_ctx_device_count(lfpsqp_ctx *ctx);
 const char *lfpsqp_last_error(lfpsqp_ctx *ctx);                    /* ctx may be NULL: last error of ctx_create */
 /* run on a caller-owned stream (e.g. torch's current stream) instead of the ctx's own; NULL restores it */
 int lfpsqp_ctx_set_stream(lfpsqp_ctx *ctx, void *cuda_stream);

@@ -34,6 +34,7 @@ EXPORTS = [
     "lfpsqp_comm_unique_id", "lfpsqp_comm_init", "lfpsqp_comm_destroy", "lfpsqp_large_retract", "lfpsqp_large_pcg",
     "lfpsqp_ineq_op", "lfpsqp_large_phase_ms", "lfpsqp_comm_ipc_export", "lfpsqp_comm_ipc_import", "lfpsqp_comm_mode",
     "lfpsqp_large_set_bounds", "lfpsqp_solve_host", "lfpsqp_linesearch", "lfpsqp_aug_hess_vec", "lfpsqp_large_projcg_general",
+    "lfpsqp_ctx_create_multi", "lfpsqp_ctx_device_count",
 ]
 
 _lib = None
@@ -56,6 +57,8 @@ def load():
         lib.lfpsqp_last_launches.argtypes = [C.c_void_p]
         lib.lfpsqp_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         lib.lfpsqp_ctx_destroy.argtypes = [C.c_void_p]
+        lib.lfpsqp_ctx_create_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+        lib.lfpsqp_ctx_device_count.argtypes = [C.c_void_p]
         lib.lfpsqp_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         P = C.c_void_p
         I = C.c_int64
@@ -135,6 +138,26 @@ class Context:
     @property
     def last_launches(self):
         return self.lib.lfpsqp_last_launches(self.h)
+
+
+class MultiContext(Context):
+    """lfpsqp_ctx_create_multi: one ctx over a device list; lfpsqp_solve_batched shards the instances over the devices
+    from one host call (one host thread per device inside the library, no collective)."""
+
+    def __init__(self, devices):
+        self.lib = load()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = self.lib.lfpsqp_ctx_create_multi(devs, len(devices), C.byref(h))
+        if rc != 0:
+            raise LFPSQPError(self.lib.lfpsqp_last_error(None).decode() or "lfpsqp_ctx_create_multi failed (rc=%d)" % rc)
+        self.h = h
+        self.device = int(devices[0])
+        self.devices = [int(d) for d in devices]
+
+    @property
+    def device_count(self):
+        return self.lib.lfpsqp_ctx_device_count(self.h)
 
 
 _default_ctx = {}

@@ -14,6 +14,10 @@
 using namespace lfpsqp;
 
 int launch_batched_reg(lfpsqp_ctx *c, lfpsqp::BatchedArgs &A);  // batched_reg.cu
+int solve_batched_multi(lfpsqp_ctx *c, int family, int64_t n, int64_t m, int64_t p, int64_t B, const double *fam_params,
+                        int64_t fam_stride, const double *x0, const double *xl, const double *xu, const lfpsqp_params *prm,
+                        double *x_out, double *obj_hist, int64_t H, int64_t *obj_len, double *lambda, lfpsqp_term *term,
+                        lfpsqp_stats *stats);   // multi.cu
 
 static_assert(sizeof(lfpsqp_params) == 160, "lfpsqp_params layout is part of the ABI");
 static_assert(sizeof(lfpsqp_term) == 40, "TerminationInfo is {Int32, pad, 3 x Float64, Int64} = 40 B");
@@ -88,6 +92,8 @@ extern "C" int lfpsqp_ctx_create(int device, lfpsqp_ctx **out) {
 
 extern "C" void lfpsqp_ctx_destroy(lfpsqp_ctx *c) {
   if (!c) return;
+  for (lfpsqp_ctx *ch : c->children) lfpsqp_ctx_destroy(ch);
+  c->children.clear();
   cudaSetDevice(c->device);
   lfpsqp_large_release(c);
   lfpsqp_comm_destroy(c);
@@ -262,7 +268,8 @@ static int prepare_batched(lfpsqp_ctx *c, int family, int64_t n, int64_t m, int6
   int rc = check_common(c, family, n, m, p, B, prm, H);
   if (rc) return rc;
   cudaSetDevice(c->device);
-  std::vector<double> bnd;
+  std::vector<double> &bnd = c->bnd_host;   // kept for the launcher (kernel selection looks at the bound kinds)
+  bnd.clear();
   int ineq = build_bounds(n, p, xl, xu, bnd);
   if (ineq == LFPSQP_ERR_BOUNDS) return c->fail(ineq, "Infeasible: lower bounds cannot be greater than upper bounds");
   if (ineq < 0) return c->fail(ineq, "xl, xu, and x0 must all be the same length (both or neither may be NULL)");
@@ -272,7 +279,6 @@ static int prepare_batched(lfpsqp_ctx *c, int family, int64_t n, int64_t m, int6
     double *dbnd = (double *)c->arena(0, bnd.size() * 8);
     if (!dbnd) return c->fail(LFPSQP_ERR_NOMEM, "device allocation failed");
     cudaMemcpyAsync(dbnd, bnd.data(), bnd.size() * 8, cudaMemcpyHostToDevice, c->stream);
-    cudaStreamSynchronize(c->stream);  // bnd is a stack-owned host vector
     A.bnd = dbnd;
   }
   return LFPSQP_OK;
@@ -292,6 +298,7 @@ extern "C" int lfpsqp_solve_batched_dev(lfpsqp_ctx *c, int family, int64_t n, in
   A.fam_params = fam_params_dev; A.fam_stride = fam_stride; A.x0 = x0_dev;
   A.x_out = x_out_dev; A.obj_hist = obj_hist_dev; A.obj_len = obj_len_dev; A.lambda = lambda_dev;
   A.term = term_dev; A.stats = stats_dev;
+  cudaMemsetAsync(obj_hist_dev, 0xff, (size_t)H * B * 8, c->stream);   // NaN-fill the unused tail of the history, as the host entry does
   rc = dispatch_batched(c, A);
   if (rc) return rc;
   cudaError_t e = cudaStreamSynchronize(c->stream);
@@ -307,6 +314,8 @@ extern "C" int lfpsqp_solve_batched(lfpsqp_ctx *c, int family, int64_t n, int64_
                                     const double *fam_params, int64_t fam_stride, const double *x0, const double *xl,
                                     const double *xu, const lfpsqp_params *prm, double *x_out, double *obj_hist,
                                     int64_t H, int64_t *obj_len, double *lambda, lfpsqp_term *term, lfpsqp_stats *stats) {
+  if (c && !c->children.empty())   // multi-GPU ctx: contiguous instance ranges per device, one host thread each (multi.cu)
+    return solve_batched_multi(c, family, n, m, p, B, fam_params, fam_stride, x0, xl, xu, prm, x_out, obj_hist, H, obj_len, lambda, term, stats);
   BatchedArgs A0;
   int rc = prepare_batched(c, family, n, m, p, B, xl, xu, prm, H, A0);
   if (rc) return rc;

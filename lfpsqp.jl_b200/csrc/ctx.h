@@ -33,6 +33,10 @@ struct lfpsqp_ctx {
   std::vector<size_t> caps;
   LargeState *large = nullptr;
   CommState comm;
+  // multi-GPU context (lfpsqp_ctx_create_multi): one child ctx per device; batched solves shard contiguous instance ranges
+  // over the children from one host call (one host thread per device, no collective).  Empty for a single-GPU ctx.
+  std::vector<lfpsqp_ctx *> children;
+  std::vector<double> bnd_host;   // host copy of the bound table of the current batched call: [kind | q | r | s | t] x NA
 
   int fail(int code, const char *fmt, ...);
   int cuda_fail(cudaError_t e, const char *what);

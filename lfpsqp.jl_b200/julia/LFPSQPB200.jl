@@ -6,7 +6,8 @@
 module LFPSQPB200
 import Random
 
-export optimize, optimize_batched, optimize_large, LFPSQPParams, TerminationInfo, DeviceFamily, rosenbrock, readme_equality,
+export optimize, optimize_batched, optimize_large, LFPSQPParams, TerminationInfo, DeviceFamily, DeviceCallback, callbacks, use_devices!,
+       rosenbrock, readme_equality,
        readme_inequality, thomson, diagquad
 
 const lib = joinpath(@__DIR__, "..", "liblfpsqp_b200.so")
@@ -77,6 +78,70 @@ function optimize(fam::DeviceFamily, x0::Vector{Float64}, xl, xu, param::LFPSQPP
     x[:, 1], obj[1:len[1], 1], λ[:, 1], TerminationInfo(TerminationCondition(t.condition), t.f_diff, t.step_diff, t.kkt_diff, t.iter)
 end
 optimize(fam::DeviceFamily, x0::Vector{Float64}, param::LFPSQPParams=LFPSQPParams()) = optimize(fam, x0, nothing, nothing, param)
+
+# ---------------------------------------------------------------------------------------------------------------
+# The reference's own method family (src/optimize.jl:13, :83, :88, :107, :112) with DEVICE-CALLBACK HANDLES in the
+# positions of the closures f, c!, d!: `cb = callbacks(fam)` gives `cb.f`, `cb.c!`, `cb.d!` (nothing when the family has
+# no such role), and then
+#     x, obj_values, λ_kkt, term_info = optimize(cb.f, cb.c!, cb.d!, x0, xl, xu, m, p)          # the north-star shape
+# is the call a user of LFPSQP.jl writes today, argument for argument (same order, same `nothing` conventions, same
+# error() conditions, same 4-tuple with the untruncated λ of length m+p, optimize.jl:67-70).  lfpsqp.jl_b200/api.py is
+# the executed mirror of exactly these methods.
+struct DeviceCallback
+    family::DeviceFamily
+    role::Symbol                  # :f, :c, :d
+end
+callbacks(fam::DeviceFamily) = (f = DeviceCallback(fam, :f), c! = fam.m > 0 ? DeviceCallback(fam, :c) : nothing,
+                                d! = fam.p > 0 ? DeviceCallback(fam, :d) : nothing)
+function _family(f::DeviceCallback, c!, d!)
+    f.role == :f || error("f must be the f handle of a registered device family")
+    for (cb, role) in ((c!, :c), (d!, :d))
+        isnothing(cb) && continue
+        (cb isa DeviceCallback && cb.family === f.family && cb.role == role) || error("$(role)! must be the $(role) handle of the same family as f")
+    end
+    f.family
+end
+function _solve(fam::DeviceFamily, x0, xl, xu, m, p, param)
+    (length(x0), m, p) == (fam.n, fam.m, fam.p) || error("sizes (n=$(length(x0)), m=$m, p=$p) do not match the family")
+    optimize(fam, x0, xl, xu, param)
+end
+# optimize(f, c!, d!, dl, du, x0, xl, xu, m, p[, param])                                             (optimize.jl:13)
+function optimize(f::DeviceCallback, c!, d!, dl, du, x0::Vector{Float64}, xl, xu, m::Int64, p::Int64, param::LFPSQPParams=LFPSQPParams())
+    fam = _family(f, c!, d!)
+    if isnothing(d!) || p == 0                                                                        # optimize.jl:15-17
+        return optimize(f, c!, x0, xl, xu, m, param)
+    end
+    (length(dl) == length(du) == p) || error("Bound vectors dl and du must be of size p")             # optimize.jl:19-21
+    (all(==(-Inf), dl) && all(==(0.0), du)) || error("only d(x) <= 0 (dl = -Inf, du = 0; optimize.jl:83-85) is on the device path")
+    n = length(x0)
+    _solve(fam, x0, isnothing(xl) ? fill(-Inf, n) : xl, isnothing(xu) ? fill(Inf, n) : xu, m, p, param)   # optimize.jl:30-36
+end
+# optimize(f, c!, d!, x0, xl, xu, m, p[, param])                                                     (optimize.jl:83-85)
+optimize(f::DeviceCallback, c!, d!, x0::Vector{Float64}, xl, xu, m::Int64, p::Int64, param::LFPSQPParams=LFPSQPParams()) =
+    optimize(f, c!, d!, fill(-Inf, p), zeros(p), x0, xl, xu, m, p, param)
+# optimize(f, c!, x0, xl, xu, m[, param])                                                            (optimize.jl:88-104)
+function optimize(f::DeviceCallback, c!, x0::Vector{Float64}, xl, xu, m::Int64, param::LFPSQPParams=LFPSQPParams())
+    fam = _family(f, c!, nothing)
+    if !isnothing(xl) && !isnothing(xu) && !(length(xl) == length(xu) == length(x0))
+        error("xl, xu, and x0 must all be the same length")                                           # optimize.jl:144-148
+    end
+    isnothing(xl) == isnothing(xu) || error("xl and xu must both be given or both be nothing")
+    _solve(fam, x0, xl, xu, m, 0, param)
+end
+# optimize(f, c!, x0, m[, param]) and optimize(f, x0[, param])                                        (optimize.jl:107-114)
+optimize(f::DeviceCallback, c!, x0::Vector{Float64}, m::Int64, param::LFPSQPParams=LFPSQPParams()) = optimize(f, c!, x0, nothing, nothing, m, param)
+optimize(f::DeviceCallback, x0::Vector{Float64}, param::LFPSQPParams=LFPSQPParams()) = optimize(f, nothing, x0, nothing, nothing, 0, param)
+
+# Multi-GPU context (lfpsqp_ctx_create_multi): every later optimize_batched call shards its instances over `devices` from one
+# host call (one host thread and one stream pipeline per device inside the library, no collective).
+function use_devices!(devices::Vector{<:Integer})
+    ctx[] == C_NULL || ccall((:lfpsqp_ctx_destroy, lib), Cvoid, (Ptr{Cvoid},), ctx[])
+    ctx[] = C_NULL
+    devs = Cint.(devices)
+    rc = ccall((:lfpsqp_ctx_create_multi, lib), Cint, (Ptr{Cint}, Cint, Ptr{Ptr{Cvoid}}), devs, length(devs), ctx)
+    rc == 0 || error(unsafe_string(ccall((:lfpsqp_last_error, lib), Cstring, (Ptr{Cvoid},), C_NULL)))
+    nothing
+end
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -974,6 +974,19 @@ extern "C" int orc_projcg_dense(int64_t n, int64_t mU, const double *A, const do
   return 0;
 }
 
+/* projcg! with a DIAGONAL operator A = diag(hd) (the Lagrangian Hessian of the DIAGQUAD / C5 family is diagonal: the
+ * reference's hess_lag_vec! closure would be an elementwise product) and a dense orthonormal U: the reference's projected
+ * CG at the BASELINE C5 shape without materialising an n x n matrix.  Used by bench.py's large-n cpu_baseline. */
+extern "C" int orc_projcg_diag(int64_t n, int64_t mU, const double *hd, const double *U, const double *b, const double *c,
+                               double tol, int64_t maxit, double *x, double *lam, int64_t *iters, double *nr) {
+  ProjCGWork w(n, mU);
+  LinOp op = [&](double *dest, const double *src) { for (int64_t i = 0; i < n; i++) dest[i] = hd[i] * src[i]; g_flops += (double)n; };
+  DenseProjector P(U, n, mU);
+  if (maxit < 0) maxit = n + mU;
+  projcg(x, lam, op, P, b, c, n, mU, tol, maxit, w, iters, nr);
+  return 0;
+}
+
 extern "C" int orc_pcg_dense(int64_t m, int64_t n, double mu, const double *J, double *x, double *r, double tol,
                              int64_t maxiter, int64_t *iters) {
   vec p(n), z(n), tmp(m);

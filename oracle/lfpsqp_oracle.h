@@ -90,6 +90,10 @@ int orc_optimize_batched(int family, const double *fam_params, int64_t fam_strid
 int orc_projcg_dense(int64_t n, int64_t mU, const double *A, const double *U, const double *b, const double *c,
                      double tol, int64_t maxit, double *x, double *lam, int64_t *iters, double *nr);
 
+/* same with a diagonal operator A = diag(hd) (n doubles) */
+int orc_projcg_diag(int64_t n, int64_t mU, const double *hd, const double *U, const double *b, const double *c,
+                    double tol, int64_t maxit, double *x, double *lam, int64_t *iters, double *nr);
+
 /* pcg! (src/retractions.jl:179-246) with dense J (m x n col-major), no preconditioner. x in/out, r in/out. */
 int orc_pcg_dense(int64_t m, int64_t n, double mu, const double *J, double *x, double *r, double tol, int64_t maxiter,
                   int64_t *iters);

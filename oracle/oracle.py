@@ -169,6 +169,19 @@ def projcg_dense(A, U, b, c, tol=1e-6, maxit=-1):
     return x, lam, it.value, nr.value
 
 
+def projcg_diag(hd, U, b, c, tol=1e-6, maxit=-1):
+    """projcg! with A = diag(hd) and orthonormal U (n x m, Fortran order): returns x, lam, iters, nr."""
+    L = lib()
+    n, mU = U.shape
+    if not U.flags.f_contiguous:
+        U = np.asfortranarray(U, dtype=np.float64)
+    hd = _f64(hd); b = _f64(b); c = _f64(c)
+    x = np.zeros(n); lam = np.zeros(mU); it = C.c_int64(0); nr = C.c_double(0)
+    L.orc_projcg_diag(C.c_int64(n), C.c_int64(mU), _dp(hd), _dp(U), _dp(b), _dp(c), C.c_double(tol), C.c_int64(maxit),
+                      _dp(x), _dp(lam), C.byref(it), C.byref(nr))
+    return x, lam, it.value, nr.value
+
+
 def pcg_dense(J, mu, b, tol=1e-6, maxiter=100):
     """pcg! (src/retractions.jl:179-246): returns x, r, flag, iters."""
     L = lib()

@@ -83,8 +83,15 @@ def fmt(res):
             % res)
 
 
-def classify(gpu, oracle_runs, label, extra=None):
+def subset(res, idx):
+    return tuple(a[idx] for a in res[:5])
+
+
+def classify(gpu, oracle_runs, label, extra=None, probe=None):
     """Per-instance verdict.  oracle_runs: dict build-name -> result tuple, first entry = the reference build ("base").
+    probe(idx) (optional) re-runs the BASE oracle on the instances idx with every input moved by one ulp (up, then down)
+    and returns the result tuples: an instance whose result moves beyond the tolerances under a 1-ulp input change is
+    ill-conditioned as a map input -> result (condition number > tolerance / 2^-52), i.e. rounding-sensitive by definition.
     Returns a JSON-able record; record["failures"] must be 0 for parity to be green."""
     names = list(oracle_runs)
     base = oracle_runs[names[0]]
@@ -103,6 +110,16 @@ def classify(gpu, oracle_runs, label, extra=None):
     bad = ~ok
     tagged = bad & (sens | ok_any)
     failed = bad & ~tagged
+    probed = 0
+    if probe is not None and failed.any():
+        idx = np.nonzero(failed)[0]
+        bsub = subset(base, idx)
+        moved = np.zeros(idx.size, dtype=bool)
+        for res in probe(idx):
+            moved |= ~within(res, bsub)
+        probed = int(idx.size)
+        tagged[idx[moved]] = True
+        failed = bad & ~tagged
     rec = dict(label=label, instances=int(B), oracle_builds=names,
                cond_frac=float(cond_ok.mean()), iter_exact_frac=float((it_diff == 0).mean()),
                iter_pm1_frac=float((it_diff <= 1).mean()), x_frac=float((x_err <= X_RTOL).mean()),
@@ -110,6 +127,7 @@ def classify(gpu, oracle_runs, label, extra=None):
                within_tolerance_frac=float(ok.mean()),
                rounding_sensitive_in_oracle=int(sens.sum()),
                outside_tolerance=int(bad.sum()), tagged_rounding_sensitive=int(tagged.sum()), failures=int(failed.sum()),
+               probed_with_one_ulp_input_change=probed,
                x_err_max=float(np.nanmax(x_err)), x_err_max_within=float(x_err[ok].max()) if ok.any() else None,
                f_err_max=float(np.nanmax(f_err)), lam_err_max=float(np.nanmax(lam_err)),
                status_nonzero=int((gpu[4]["status"] != 0).sum()),
@@ -149,7 +167,9 @@ def record(rec):
         data = {"criteria": {"condition": "equal", "iterations": "+-1", "x_rel": X_RTOL, "f_rel": F_RTOL,
                              "classification": "outside tolerance -> rounding-sensitive iff two builds of the oracle "
                                                "(plain / fma / seq summation) disagree on that instance beyond the same "
-                                               "tolerances, or the GPU matches one of those builds; else FAILURE"},
+                                               "tolerances, or the GPU matches one of those builds, or the plain oracle's "
+                                               "own result moves beyond the tolerances when its input is changed by one "
+                                               "ulp; else FAILURE"},
                 "records": {}}
     data["records"][rec["label"]] = rec
     data["failures_total"] = int(sum(r.get("failures", 0) for r in data["records"].values()))

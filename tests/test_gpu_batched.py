@@ -254,3 +254,26 @@ def test_rank_deficient_jacobian_vs_oracle(L, oracle):
     print(fmt(res)); print(fmt(base))
     assert np.all(gpu[4]["status"] & 1) and np.all(gpu[3] == 0.0)          # lambda = 0 beyond the rank
     assert res["cond_frac"] >= base["cond_frac"] - 0.05 and res["all_ok_frac"] >= base["all_ok_frac"] - 0.1
+
+
+def test_multi_device_context_shards_instances(L, oracle):
+    # lfpsqp_ctx_create_multi (SURVEY 8b "context (device list)"): one host call, contiguous instance ranges per device, no
+    # collective.  Runs over every visible GPU (a 1-GPU box exercises the same code with one child); results must be
+    # IDENTICAL to the single-device call (same kernels, same instances) and the ranges must tile the batch.
+    import torch
+    ndev = torch.cuda.device_count()
+    rng = np.random.default_rng(41)
+    B, n = 1000 + 7, 50                      # not divisible by the device count
+    co = rng.standard_normal((B, n)); inf = np.inf * np.ones(n)
+    fam = L.families.readme_inequality(co)
+    ref = L.optimize_batched(fam.f, None, fam.d, np.zeros((B, n)), -inf, inf, 0, 1, return_stats=True)
+    for devs in ([0], list(range(ndev))):
+        mc = L.MultiContext(devs)
+        assert mc.device_count == len(devs)
+        out = L.optimize_batched(fam.f, None, fam.d, np.zeros((B, n)), -inf, inf, 0, 1, ctx=mc, return_stats=True)
+        assert np.array_equal(out[0], ref[0]) and np.array_equal(out[3], ref[3])
+        assert np.array_equal(out[4]["iter"], ref[4]["iter"]) and np.array_equal(out[4]["condition"], ref[4]["condition"])
+        assert np.array_equal(out[2], ref[2]) and np.array_equal(out[5]["retract_pcg"], ref[5]["retract_pcg"])
+        mc.close()
+    with pytest.raises(L.LFPSQPError):
+        L.MultiContext([0, 0])               # each device once

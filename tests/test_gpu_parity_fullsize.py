@@ -44,7 +44,12 @@ def test_c2_all_65536_bench_instances(L, oracle):
     runs = _oracle_builds(oracle, lambda: oracle.optimize_batched("readme_ineq", n, 0, 1, x0, xl=-inf, xu=inf, fam_params=coeff,
                                                                  fam_stride=n, H=bench.HIST, nthreads=bench.host_cores()))
     nc = np.linalg.norm(coeff, axis=1)
-    rec = parity.classify(gpu, runs, "C2 README inequality, all %d bench instances" % B,
+
+    def probe(idx):
+        for to in (np.inf, -np.inf):
+            yield oracle.optimize_batched("readme_ineq", n, 0, 1, x0[idx], xl=-inf, xu=inf, fam_params=np.nextafter(coeff[idx], to),
+                                          fam_stride=n, H=bench.HIST, nthreads=bench.host_cores())
+    rec = parity.classify(gpu, runs, "C2 README inequality, all %d bench instances" % B, probe=probe,
                           extra={"max_dist_to_known_solution": float(np.max(np.linalg.norm(gpu[0] + coeff / nc[:, None], axis=1))),
                                  "gpu_stats_equal_oracle": {k: float((gpu[5][k] == runs["base"][5][k]).mean())
                                                             for k in ("retract_outer", "retract_pcg", "armijo_trials", "pp_backtracks",
@@ -65,7 +70,11 @@ def test_c3_all_1048576_bench_instances(L, oracle):
     gpu = L.optimize_batched(fam.f, x0, history=H)
     runs = _oracle_builds(oracle, lambda: oracle.optimize_batched("rosenbrock", 2, 0, 0, x0, H=H, nthreads=bench.host_cores()))
     t0 = gpu[4][0]
-    rec = parity.classify(gpu, runs, "C3 Rosenbrock, all %d bench instances" % B,
+
+    def probe(idx):
+        for to in (np.inf, -np.inf):
+            yield oracle.optimize_batched("rosenbrock", 2, 0, 0, np.nextafter(x0[idx], to), H=H, nthreads=bench.host_cores())
+    rec = parity.classify(gpu, runs, "C3 Rosenbrock, all %d bench instances" % B, probe=probe,
                           extra={"golden_instance0": {"iter": int(t0["iter"]), "condition": int(t0["condition"]), "f_diff": float(t0["f_diff"])}})
     parity.record(rec)
     assert int(t0["iter"]) == 17 and int(t0["condition"]) == 0 and abs(float(t0["f_diff"]) - 1.0898882046786806e-7) < 1e-15
