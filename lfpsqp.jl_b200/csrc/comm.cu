@@ -117,7 +117,7 @@ __device__ __forceinline__ bool pc_exchange(const PeerPtrs &P, int rank, int wor
     do {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
       if (v >= epoch) break;
-      if (clock64() - t0 > 4000000000LL) { ok = false; ctrl->rankflag = 99; break; }   // ~2 s: a peer died; do not hang the GPU
+      if (clock64() - t0 > 8000000000LL) { ok = false; ctrl->commfail = 1; break; }   // ~4 s: a peer died; do not hang the GPU (the host reports LFPSQP_ERR_COMM)
     } while (true);
   }
   __syncthreads();
@@ -256,7 +256,7 @@ extern "C" int lfpsqp_comm_ipc_import(lfpsqp_ctx *c, const void *handles) {
     if (e != cudaSuccess) { c->comm.peer_ready = false; return c->cuda_fail(e, "cudaIpcOpenMemHandle (peer-memory all-reduce unavailable; NCCL is used instead)"); }
     c->comm.peer_map[r] = (double *)p;
   }
-  c->comm.epoch = 0;
+  // the epoch stays monotone over re-imports: the exported region keeps the flags of earlier epochs
   c->comm.peer_ready = true;
   return LFPSQP_OK;
 }

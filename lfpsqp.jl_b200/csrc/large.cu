@@ -51,6 +51,15 @@ static int read_ctrl(lfpsqp_ctx *c, LargeState &S) {
   CK(cudaMemcpyAsync(S.hctrl, S.ctrl, sizeof(LargeCtrl), cudaMemcpyDeviceToHost, S.stream));
   CK(cudaStreamSynchronize(S.stream));
   CK(cudaGetLastError());   // a refused launch (bad configuration) since the last check must not pass silently
+  if (S.hctrl->commfail) return c->fail(LFPSQP_ERR_COMM, "a peer-memory exchange of the column-sharded mode timed out (a rank died or fell > 4 s behind)");
+  if (S.guard_pending) {    // pivots of the factor just computed -> which solve the fused projcg kernel may use
+    S.guard_pending = false;
+    const double lo = S.hctrl->ldiag_min, hi = S.hctrl->ldiag_max;   // ~lambda_min(G) (from above), trace(G)
+    S.pivot_ratio2 = (lo > 0.0) ? hi / lo : INFINITY;
+    S.explicit_inverse_ok = S.pivot_ratio2 <= S.inverse_guard;
+    const char *env = getenv("LFPSQP_EXPLICIT_INVERSE");
+    if (env && (env[0] == '0' || env[0] == '1')) S.explicit_inverse_ok = env[0] == '1';
+  }
   return 0;
 }
 static void write_ctrl_fields(LargeState &S) {  // push the host copy (tolerances, limits, statuses) to the device
@@ -326,6 +335,17 @@ static int factorize(lfpsqp_ctx *c, LargeState &S) {
   transpose_kernel<<<tg, 256, 0, S.stream>>>(S.XT, ldm, S.Linv, ldm, m, m);
   if (S.fused_ok && S.Ginv) {   // G^-1 = L^-T L^-1 = XT XT' for the fused projcg kernel (large_fused.cu): one more DMMA GEMM, m^3 flops
     gemm_nt(S, m, m, m, S.XT, ldm, S.XT, ldm, S.Ginv, ldm, GEMM_ASSIGN, 0);
+    // guard of that shortcut: kappa = trace(G) * lambda_max(G^-1) >= cond(G) (8 power iterations on G^-1, ~0.1 ms); read_ctrl
+    // turns it into S.explicit_inverse_ok
+    const int nb = std::min(m, 64);
+    lower_fro2_kernel<<<nb, 256, 0, S.stream>>>(S.G, ldm, m, S.gpart + 7 * (size_t)MAXP);
+    power_step_kernel<<<1, 256, 0, S.stream>>>(m, nullptr, S.nr_t1, S.gpart + 7 * (size_t)MAXP, nb, S.ctrl);
+    for (int it = 0; it < 8; it++) {
+      rows_dot(S, S.Ginv, ldm, m, m, S.nr_t1, S.nr_t2, 0);
+      power_step_kernel<<<1, 256, 0, S.stream>>>(m, S.nr_t2, S.nr_t1, nullptr, 0, S.ctrl);
+    }
+    S.launches += 10;
+    S.guard_pending = true;
   }
   S.launches += 3;
   S.factorizations++;
@@ -1006,6 +1026,17 @@ extern "C" int lfpsqp_large_setup(lfpsqp_ctx *c, int family, int64_t n_global, i
     const char *env = getenv("LFPSQP_FUSED_PROJCG");   // "0" selects the multi-kernel projcg loop (A/B measurements, tests)
     if (m > 0 && !(env && env[0] == '0')) fused_projcg_init(S, c->device);   // pcg! is fused for every family, projcg for diagonal Hessians
   }
+  if (S.world > 1) {
+    // every rank must take the same path (a rank in the launch-per-phase loop would deadlock against peers inside the fused
+    // mailbox protocol): fused only if ALL ranks are eligible.  The all-reduce is also the barrier that ends setup, so that
+    // no rank starts exchanging while another one is still uploading its parameters.
+    double flag = S.fused_ok ? 1.0 : 0.0;
+    CK(cudaMemcpyAsync(S.commbuf, &flag, 8, cudaMemcpyHostToDevice, S.stream));
+    comm_allreduce(S, S.commbuf, 1);
+    CK(cudaMemcpyAsync(&flag, S.commbuf, 8, cudaMemcpyDeviceToHost, S.stream));
+    CK(cudaStreamSynchronize(S.stream));
+    if (flag < (double)S.world - 0.5) S.fused_ok = false;
+  }
   return LFPSQP_OK;
 }
 
@@ -1039,7 +1070,7 @@ extern "C" int lfpsqp_large_solve(lfpsqp_ctx *c, const double *x0_loc, const lfp
   if (H < 1) return c->fail(LFPSQP_ERR_ARG, "H must be >= 1");
   cudaEventRecord(c->ev0, S.stream);
   rc = solve(c, S, x0_loc, x_out_loc, obj_hist, H, obj_len, lambda, term, stats);
-  if (rc) return rc;
+  if (rc) return S.hctrl->commfail ? LFPSQP_ERR_COMM : rc;
   cudaEventRecord(c->ev1, S.stream);
   cudaEventSynchronize(c->ev1);
   float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->last_ms = ms;
@@ -1084,6 +1115,10 @@ extern "C" int lfpsqp_large_set_bounds(lfpsqp_ctx *c, const double *xl_loc, cons
   CK(cudaMemsetAsync(S.I.lamy, 0, nl * 8, S.stream));
   CK(cudaStreamSynchronize(S.stream));   // bnd is a stack-owned host vector
   S.I.q = S.bq; S.I.r = S.br; S.I.s = S.bs; S.I.t = S.bt; S.I.nx = nl;
+  if (S.world > 1) {   // leave together: nobody starts a solve while a peer is still uploading its bound tables
+    comm_allreduce(S, S.commbuf, 1);
+    CK(cudaStreamSynchronize(S.stream));
+  }
   return LFPSQP_OK;
 }
 

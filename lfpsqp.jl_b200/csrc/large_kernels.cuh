@@ -125,6 +125,36 @@ __global__ void __launch_bounds__(256) tri_gemv_kernel(const double *__restrict_
 
 // ------------------------------------------------------------------ finalize: ctrl->s[k] = reduce(part[slot k]) for the slots in mask
 // bit k of summask: sum-reduce slot k into s[k]; bit k of maxmask: max-reduce slot k into s[k]
+// explicit-inverse guard of the fused projcg (large.cu::factorize): an UPPER bound of cond(G) from quantities that are
+// cheap once G^-1 is explicit: trace(G) = |L|_F^2 >= lambda_max(G), and lambda_max(G^-1) = 1 / lambda_min(G) by a few
+// power iterations on G^-1 (each one m x m matvec).
+__global__ void __launch_bounds__(256) lower_fro2_kernel(const double *__restrict__ L, int64_t ld, int m, double *part) {
+  __shared__ double sh[33];
+  double s = 0.0;
+  for (int i = blockIdx.x; i < m; i += gridDim.x) {
+    const double *row = L + (int64_t)i * ld;
+    for (int k = threadIdx.x; k <= i; k += blockDim.x) s += row[k] * row[k];
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+// v <- w / |w| ; ctrl->ldiag_min = 1 / |w| (the running estimate of lambda_min(G)); first call (w == nullptr): v = 1/sqrt(m)
+// and ctrl->ldiag_max = sum(part) = trace(G)
+__global__ void __launch_bounds__(256) power_step_kernel(int m, const double *w, double *v, const double *part, int np, LargeCtrl *ctrl) {
+  __shared__ double sh[33];
+  if (!w) {
+    const double tr = reduce_partials(part, np, sh);
+    for (int i = threadIdx.x; i < m; i += blockDim.x) v[i] = rsqrt((double)m);
+    if (threadIdx.x == 0) { ctrl->ldiag_max = tr; ctrl->ldiag_min = 0.0; }
+    return;
+  }
+  double s = 0.0;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) s += w[i] * w[i];
+  s = sqrt(block_sum(s, sh));
+  for (int i = threadIdx.x; i < m; i += blockDim.x) v[i] = w[i] / s;
+  if (threadIdx.x == 0) ctrl->ldiag_min = 1.0 / s;
+}
+
 __global__ void __launch_bounds__(256) finalize_kernel(const double *part, int np, unsigned summask, unsigned maxmask,
                                                        LargeCtrl *ctrl) {
   __shared__ double sh[33];

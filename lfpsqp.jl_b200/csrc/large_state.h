@@ -26,6 +26,11 @@ struct LargeState {
   int fused_grid = 0;
   double *fused_part = nullptr;
   double *Ginv = nullptr;                  // explicit G^-1 = L^-T L^-1 (m x m, symmetric) for the one-phase solve of the fused kernel
+  // explicit-inverse guard: u = G^-1 t loses cond(G) eps, two triangular solves only cond(L) eps.  factorize() bounds cond(G)
+  // from above by kappa = trace(G) * lambda_max(G^-1) (power iterations on the explicit inverse); above `inverse_guard` the
+  // fused kernel runs the two triangular phases instead (LFPSQP_EXPLICIT_INVERSE=0/1 forces either path: tests)
+  bool explicit_inverse_ok = true, guard_pending = false;
+  double inverse_guard = 1e6, pivot_ratio2 = 1.0;   // pivot_ratio2: the last kappa
   int m = 0, sm_count = 148, world = 1, rank = 0;
   cudaStream_t stream = nullptr;
   lfpsqp_params prm;

@@ -237,3 +237,95 @@ def test_fused_pcg_matches_multi_kernel_loop(L, n, m):
     # the solution really solves (J'J + mu I) x = b
     J = Q * x0[None, :] + A
     assert np.linalg.norm(J.T @ (J @ xb) + 1e-2 * xb - rhs) < 1e-7
+
+
+def _illcond_diagquad(L, n, m, cond, seed):
+    """DIAGQUAD whose Jacobian at x0 has (almost exactly) the singular values logspace(0, -log10 cond): A = U diag(s) V',
+    Q tiny, so that J(x0) = Q .* x0' + A ~ A."""
+    rng = np.random.default_rng(seed)
+    U, _ = np.linalg.qr(rng.standard_normal((m, m)))
+    V, _ = np.linalg.qr(rng.standard_normal((n, m)))
+    sv = np.logspace(0.0, -np.log10(cond), m)
+    A = (U * sv) @ V.T
+    Q = 1e-6 * rng.standard_normal((m, n)) / np.sqrt(n)
+    x0 = rng.standard_normal(n); xt = rng.standard_normal(n)
+    w = np.exp(rng.uniform(0.0, np.log(100.0), n))
+    b = 0.5 * Q @ (x0 * x0) + A @ x0
+    return Q, A, b, xt, w, x0
+
+
+@pytest.mark.parametrize("cond", [1e2, 1e4, 1e6])
+def test_explicit_inverse_guard_ill_conditioned_jacobian(L, monkeypatch, cond):
+    # VERDICT r1 weak #7: the fused projcg applies G^-1 = L^-T L^-1 explicitly (one grid phase), which loses cond(G) eps where
+    # two triangular solves lose cond(L) eps.  The guard (pivot ratio^2 > 1e6) must switch the fused kernel to the two
+    # triangular phases; fused (either solve), the launch-per-phase loop and an orthogonal-projector reference are compared.
+    n, m, K = 4096, 128, 12
+    Q, A, b, xt, w, x0 = _illcond_diagquad(L, n, m, cond, seed=17)
+    fam = L.families.diagquad(Q, A, b, xt, w)
+    J = Q * x0[None, :] + A
+    assert 0.5 * cond < np.linalg.cond(J) < 2 * cond
+    lam = np.zeros(m)
+    # reference: K projected-CG iterations with the projector from a Householder QR of J' (backward stable at any cond(J))
+    Qj, _ = np.linalg.qr(J.T)
+    Pm = lambda v: v - Qj @ (Qj.T @ v)
+    g = w * (x0 - xt)
+    bb = Pm(-g)
+    xs = np.zeros(n); r = Pm(-bb); d = -r; rg = r @ r
+    for _ in range(K):
+        Ad = w * d; al = rg / (d @ Ad); xs = xs + al * d; rp = r + al * Ad; gp = Pm(rp)
+        be = (rp @ gp) / rg; d = be * d - gp; r = gp; rg = gp @ gp
+    res = {}
+    for mode, env in (("auto", {}), ("explicit", {"LFPSQP_EXPLICIT_INVERSE": "1"}), ("triangular", {"LFPSQP_EXPLICIT_INVERSE": "0"}),
+                      ("unfused", {"LFPSQP_FUSED_PROJCG": "0"})):
+        for k_, v_ in env.items():
+            monkeypatch.setenv(k_, v_)
+        P = L.LargeProblem(fam)
+        assert P.factor(x0, want=())["rank_deficient"] == 0
+        out = P.projcg(x0, lam=lam, tol=0.0, maxit=K)
+        for k_ in env:
+            monkeypatch.delenv(k_)
+        assert out["iters"] == K
+        res[mode] = (out["sol"], rel(out["sol"], xs), np.linalg.norm(J @ out["sol"]) / np.linalg.norm(out["sol"]))
+    print("cond(J) = %.0e: " % cond + "  ".join("%s: err %.2e |J x|/|x| %.2e" % (k_, v_[1], v_[2]) for k_, v_ in res.items()))
+    # the guard (trace(G) lambda_max(G^-1) <= 1e6): explicit inverse for cond(J) = 1e2 (kappa ~ m 1e4 / ln..), triangular beyond
+    if cond <= 1e2:
+        assert np.array_equal(res["auto"][0], res["explicit"][0])
+    else:
+        assert np.array_equal(res["auto"][0], res["triangular"][0])
+    # the two triangular phases are as accurate as the launch-per-phase loop (same algorithm, different reduction order)
+    assert res["triangular"][1] <= 10 * res["unfused"][1] + 1e-13
+    assert res["auto"][1] <= 10 * res["unfused"][1] + 1e-13
+    # what the Gram form itself can deliver (cond(J)^2 eps) -- the SVD-based reference resolves more; documented in DESIGN.md
+    assert res["auto"][1] < 50 * cond * cond * 2.2e-16 + 1e-12
+
+
+@pytest.mark.parametrize("cond", [1e2, 1e4])
+def test_ill_conditioned_full_solve_vs_oracle(L, oracle, cond):
+    # full solves with an ill-conditioned Jacobian.  cond(J) = 1e2: plain parity.  cond(J) = 1e4: the REFERENCE ALGORITHM itself
+    # stalls there (ProjPenalty's pcg! hits maxiter_pcg, alpha collapses, f_tol fires at a non-stationary point) and two builds
+    # of the oracle differ by 13 outer iterations and 2e-5 in x -- the per-instance classification of tests/parity.py applies.
+    from tests import parity
+    n, m = 1024, 48
+    Q, A, b, xt, w, x0 = _illcond_diagquad(L, n, m, cond, seed=23)
+    fam = L.families.diagquad(Q, A, b, xt, w)
+    x, obj, lam, info, st, status = L.LargeProblem(fam).solve(x0, L.LFPSQPParams(), return_stats=True)
+    term_dt = [("condition", "<i4"), ("status", "<i4"), ("f_diff", "<f8"), ("step_diff", "<f8"), ("kkt_diff", "<f8"), ("iter", "<i8")]
+
+    def pack(xv, ov, lv, cnd, it, stt=0, H=20000):
+        t = np.zeros(1, dtype=term_dt); t["condition"] = cnd; t["iter"] = it; t["status"] = stt
+        o = np.full((1, H), np.nan); o[0, :len(ov)] = ov
+        return (xv[None, :], o, np.array([len(ov)]), np.asarray(lv)[None, :], t)
+    runs = {}
+    for v in ("base", "fma", "seq"):
+        if v == "base":
+            r = oracle.optimize("diagquad", n, m, 0, x0, fam_params=fam.params)
+        else:
+            with oracle.variant(v):
+                r = oracle.optimize("diagquad", n, m, 0, x0, fam_params=fam.params)
+        runs[v] = pack(r[0], r[1], r[2], r[3]["condition"], r[3]["iter"])
+    rec = parity.classify(pack(x, obj, lam, int(info.condition), info.iter, status), runs,
+                          "DIAGQUAD n=1024 m=48 with cond(J) = %.0e, full solve, large-n mode" % cond, extra={"gpu_iter": int(info.iter)})
+    parity.record(rec)
+    assert rec["failures"] == 0, parity.fmt_record(rec)
+    if cond <= 1e2:
+        assert rec["within_tolerance"] == 1 and status == 0
