@@ -53,9 +53,9 @@ typedef struct {
 enum { LFPSQP_F_TOL = 0, LFPSQP_X_TOL = 1, LFPSQP_KKT_TOL = 2, LFPSQP_MAX_ITER = 3, LFPSQP_ARMIJO_ERROR = 4 };
 
 /* per-instance status bits (in-band; 0 = the path is the reference's path) */
-#define LFPSQP_ST_RANK_DEFICIENT 1 /* the projected Jacobian lost rank at some iterate. Batched mode: informational -- the
-                                      truncated path of optimize.jl:297-302 was taken (eigen-decomposition of J W J',
-                                      pseudo-inverse); large-n mode: the solve stopped at that iterate */
+#define LFPSQP_ST_RANK_DEFICIENT 1 /* the projected Jacobian lost rank at some iterate: informational -- the truncated path of
+                                      optimize.jl:297-302 was taken (eigen-decomposition of J W J', truncated pseudo-inverse;
+                                      batched mode: in shared memory, large-n mode: one-sided Jacobi on the device) */
 #define LFPSQP_ST_NONFINITE 2      /* a non-finite iterate, or the retraction failed at every step length down to alpha < 1e-100
                                       (flag_last = 98; the reference spins forever there, src/linesearch.jl:57-60) */
 
@@ -184,6 +184,8 @@ int lfpsqp_solve_host(lfpsqp_ctx *ctx, const lfpsqp_host_callbacks *cb, int64_t 
                       int64_t H, int64_t *obj_len, double *lambda, lfpsqp_term *term, lfpsqp_stats *stats);
 /* unit-level ops mirroring the reference functions one to one (host buffers; outputs may be NULL):
  *   factor  : J = jac(x); G = J J' (m x m row-major, lower triangle valid), L = chol(G), Linv = L^-1   [ksvd!]
+ *             *rank_deficient = 0, or the rank defect when the Cholesky pivot test failed (then L / Linv are undefined and the
+ *             following project / projcg calls use the truncated pseudo-inverse, optimize.jl:297-302)
  *   project : v - J'(J J')^-1 J v and lambda = (J J')^-1 J v with the cached factor                    [kgemv! x2, optimize.jl:306-307, :333-343]
  *   projcg  : projcg! (src/projcg.jl:40-121) at x with multipliers lam on b = P(-grad f(x)), c = 0; status:
  *             1 converged, 2 negative curvature, 3 rg<=0, 4 iteration limit; ms = device time of the loop */

@@ -157,17 +157,23 @@ def optimize_batched(*args, ctx=None, history=64, return_stats=False):
                                       _lib.ptr(xu), C.cast(C.pointer(cp), C.c_void_p), _lib.ptr(x), _lib.ptr(obj), H,
                                       _lib.ptr(olen), _lib.ptr(lam), _lib.ptr(term), _lib.ptr(stats))
     ctx.check(rc)
+    if B and int(olen.max()) > H:
+        import warnings
+        warnings.warn("obj_values holds the first %d objective values per instance; the longest history has %d (the reference returns "
+                      "every iterate's objective, optimize.jl:426): pass history=maxiter+1 to keep them all" % (H, int(olen.max())))
     if return_stats:
         return x, obj, olen, lam, term, stats
     return x, obj, olen, lam, term
 
 
-def optimize(*args, ctx=None, history=20000, return_stats=False):
+def optimize(*args, ctx=None, history=None, return_stats=False):
     """optimize(f, x0[, param]) / (f, c!, x0, m[, param]) / (f, c!, x0, xl, xu, m[, param]) /
     (f, c!, d!, x0, xl, xu, m, p[, param]) / (f, c!, d!, dl, du, x0, xl, xu, m, p[, param])
     -> (x, obj_values, λ_kkt, term_info), as src/optimize.jl:442."""
     a = list(args)
     param = a.pop() if a and isinstance(a[-1], LFPSQPParams) else None
+    if history is None:     # every iterate's objective, as the reference returns (optimize.jl:250, :426)
+        history = int((param or LFPSQPParams()).maxiter) + 1
     if len(a) == 9 and callable(a[0]) and not isinstance(a[0], DeviceCallback):
         # the explicit-derivative core optimize(f, grad!, c!, jac!, hess_lag_vec!, x0, xl, xu, m, param) (optimize.jl:119)
         # with host callables: generic problems, linear algebra on the device (host.py)

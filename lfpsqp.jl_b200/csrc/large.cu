@@ -131,6 +131,12 @@ static void cols_dot(LargeState &S, const double *Jm, int64_t ld, int m, int64_t
 // u = (J J')^-1 t through the cached factor: y = L^-1 t ; u = L^-T y
 static void gram_solve(LargeState &S, const double *t, double *u, double *u_copy, int pred) {
   const int m = S.m;
+  if (S.pinv_active) {   // rank-deficient: u = G^+ t (one dense m x m pass; optimize.jl:297-302 equivalent, large_eig.cu)
+    rows_dot(S, S.Ginv, S.ldm, m, m, t, u, pred);
+    if (u_copy) vec(S, m, [=] __device__(int64_t a, double *) { u_copy[a] = u[a]; });
+    S.launches++;
+    return;
+  }
   tri_gemv_kernel<<<(m + 7) / 8, 256, m * sizeof(double), S.stream>>>(S.Linv, S.ldm, m, t, S.ty, 0, nullptr, S.ctrl, pred);
   tri_gemv_kernel<<<(m + 7) / 8, 256, m * sizeof(double), S.stream>>>(S.XT, S.ldm, m, S.ty, u, 1, u_copy, S.ctrl, pred);
   S.launches += 2;
@@ -289,6 +295,35 @@ static void y_retract(LargeState &S, double *vn, const double *vb) {  // y_retra
   S.launches++;
 }
 
+template <class T> static bool dalloc(LargeState &S, T **p, size_t count);
+static void gram_only(LargeState &S) {   // S.G (lower tiles) = J W J', all-reduced
+  const int m = S.m;
+  const double *Jg = S.ineq ? S.Jw : S.J;    // Jw = J diag(Dy) was formed by the factorize() call that precedes
+  gemm_nt(S, m, m, (int)S.n_loc, Jg, S.ldj, Jg, S.ldj, S.G, S.ldm, GEMM_ASSIGN, 1);
+  if (S.world > 1) comm_allreduce(S, S.G, (size_t)m * S.ldm);
+}
+// Truncated path of optimize.jl:297-302 in Gram form: G = V diag(lambda) V' (Jacobi, large_eig.cu), G^+ into S.Ginv.
+// regram: S.G no longer holds the Gram (a Cholesky attempt overwrote it) -> recompute it first.
+static int factorize_pinv(lfpsqp_ctx *c, LargeState &S, bool regram) {
+  const int m = S.m; const int64_t ldm = S.ldm;
+  if (!S.eigV) {
+    bool ok = dalloc(S, &S.eigV, (size_t)m * ldm) && dalloc(S, &S.eigT, (size_t)m * ldm) && dalloc(S, &S.eigLam, (size_t)m + 2) &&
+              dalloc(S, &S.eigScratch, 40);
+    if (ok && !S.Ginv) ok = dalloc(S, &S.Ginv, (size_t)m * ldm);
+    if (!ok) return c->fail(LFPSQP_ERR_NOMEM, "rank-deficient path: workspace allocation failed");
+  }
+  if (regram) gram_only(S);
+  unsigned long long *sc = S.eigScratch;
+  if (large_eig_pinv_factors(S, S.G, S.eigV, S.eigLam, 1, reinterpret_cast<int *>(sc + 34), sc, reinterpret_cast<unsigned *>(sc + 32)))
+    return c->fail(LFPSQP_ERR_CUDA, "rank-deficient path: cooperative launch of the Jacobi eigen-solver failed");
+  dim3 tg((m + 31) / 32, (m + 31) / 32);
+  transpose_kernel<<<tg, 256, 0, S.stream>>>(S.eigV, ldm, S.eigT, ldm, m, m);
+  gemm_nt(S, m, m, m, S.eigT, ldm, S.eigT, ldm, S.Ginv, ldm, GEMM_ASSIGN, 0);   // G^+ = Vs' Vs
+  S.pinv_active = true; S.prefer_pinv = true; S.explicit_inverse_ok = true; S.guard_pending = false;
+  S.launches += 2; S.factorizations++;
+  return 0;
+}
+
 // ------------------------------------------------------------------ factorisation: G = J J' = L L', XT = L^-T, Linv = L^-1
 // (with bounds G = J diag(Dy^2) J' = PJct' PJct, optimize.jl:288-289 / SURVEY App. B)
 static int factorize(lfpsqp_ctx *c, LargeState &S) {
@@ -304,6 +339,8 @@ static int factorize(lfpsqp_ctx *c, LargeState &S) {
   gemm_nt(S, m, m, (int)S.n_loc, Jg, S.ldj, Jg, S.ldj, S.G, ldm, GEMM_ASSIGN, 1);   // SYRK, lower tiles
   cudaEventRecord(S.ev_g1, S.stream);
   if (S.world > 1) comm_allreduce(S, S.G, (size_t)m * ldm);
+  if (S.prefer_pinv) return factorize_pinv(c, S, false);   // this problem lost rank before: go straight to the eigen-decomposition
+  S.pinv_active = false; S.rank_cur = m;
   diag_thresh_kernel<<<1, 256, 0, S.stream>>>(S.G, ldm, m, S.prm.eps_rank, S.thresh);
   constexpr int NB = 64;
   const size_t psm = 2 * NB * (NB + 1) * sizeof(double);
@@ -423,7 +460,8 @@ static int projcg(lfpsqp_ctx *c, LargeState &S, double tol, int64_t maxit, int c
   if (S.world > 1) comm_allreduce_loop_slot(S, 3, S.np_loop_raw);
   S.launches += 2;
   // min(maxit, n + length(c)) (projcg.jl:71): c has length rank = m, or n + rank with the bound projector (optimize.jl:366-372)
-  int64_t lim = std::min<int64_t>(maxit, S.ineq ? 3 * S.n + S.m : S.n + S.m);
+  const int64_t rk = S.pinv_active ? S.rank_cur : S.m;
+  int64_t lim = std::min<int64_t>(maxit, S.ineq ? 3 * S.n + rk : S.n + rk);
   S.hctrl->tol = tol; S.hctrl->lim = (int)std::min<int64_t>(lim, 2000000000); S.hctrl->iter = 0; S.hctrl->status = (lim > 0) ? 0 : 4;
   S.hctrl->nr = INFINITY;
   write_ctrl_fields(S);
@@ -775,6 +813,7 @@ static int solve(lfpsqp_ctx *c, LargeState &S, const double *x0_host, double *x_
   double *x = S.x, *g = S.g, *d = S.d, *xnew = S.xnew, *xtil = S.xtil, *nd = S.nd;
   S.reset_counters();
   S.cb_err = 0;
+  S.prefer_pinv = false; S.pinv_active = false; S.rank_cur = m;
   CK(cudaMemcpyAsync(x, x0_host, n * sizeof(double), cudaMemcpyHostToDevice, S.stream));
   CK(cudaMemsetAsync(g, 0, nv * sizeof(double), S.stream));                              // g[n+1:] == 0 (optimize.jl:191)
   if (m > 0) CK(cudaMemsetAsync(S.cvc, 0, m * sizeof(double), S.stream));
@@ -812,6 +851,7 @@ static int solve(lfpsqp_ctx *c, LargeState &S, const double *x0_host, double *x_
       if (m > 0) {
         fam_c_jac(S, S.J, S.cval, x);                                                   // :283
         if (factorize(c, S)) return LFPSQP_ERR_CUDA;
+        cudaMemcpyAsync(xtil, d, nv * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);   // d before the projection (rank-loss redo)
       }
       project(S, d, S.lam, 0, 1, 1);                                                    // :306-307 / :314-317, :331-343
       S.t_factor_pending = tf0;
@@ -822,7 +862,17 @@ static int solve(lfpsqp_ctx *c, LargeState &S, const double *x0_host, double *x_
     if (read_ctrl(c, S)) return LFPSQP_ERR_CUDA;
     if (S.cb_err) return LFPSQP_ERR_CALLBACK;
     if (S.t_factor_pending > 0) { S.ms_factor += now_ms() - S.t_factor_pending; S.t_factor_pending = 0; }
-    if (S.hctrl->rankflag) { status |= LFPSQP_ST_RANK_DEFICIENT; cond = LFPSQP_MAX_ITER; break; }
+    if (S.hctrl->rankflag) {
+      // the Cholesky pivot test failed: the reference's truncated path (optimize.jl:297-302, :335-340) through the
+      // eigen-decomposition of the Gram; the projection is redone with the pseudo-inverse
+      S.hctrl->rankflag = 0; write_ctrl_fields(S);
+      if (factorize_pinv(c, S, true)) return LFPSQP_ERR_CUDA;
+      cudaMemcpyAsync(d, xtil, nv * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);
+      project(S, d, S.lam, 0, 1, 1);
+      finalize(S, 1u, 8u);
+      if (read_ctrl(c, S)) return LFPSQP_ERR_CUDA;
+    }
+    if (S.pinv_active) { S.rank_cur = (int)S.hctrl->s[14]; status |= LFPSQP_ST_RANK_DEFICIENT; }   // informational, as in batched mode
     kkt_diff = S.hctrl->s[3];                                                           // :320
     double gn = sqrt(S.hctrl->s[0]);
     if (f_diff <= prm.eps_f) { cond = LFPSQP_F_TOL; break; }                            // :347-359
@@ -843,7 +893,7 @@ static int solve(lfpsqp_ctx *c, LargeState &S, const double *x0_host, double *x_
       if (S.hctrl->s[0] > 0.0) { cudaMemcpyAsync(d, nd, nv * sizeof(double), cudaMemcpyDeviceToDevice, S.stream); S.newton_accepted++; }
     }
     // :396-412 (rank == m here): NR / ProjPenalty with constraints, else YRetract with bounds, else Euclidean
-    const int kind = (m > 0) ? ((!prm.do_project_retract) ? 2 : 3) : (ineq ? 1 : 0);
+    const int kind = (m > 0) ? ((!prm.do_project_retract && !(S.pinv_active && S.rank_cur < m)) ? 2 : 3) : (ineq ? 1 : 0);
     // armijo! (linesearch.jl:32-89)
     vec(S, nv, [=] __device__(int64_t i, double *acc) { acc[0] += d[i] * g[i]; }, 0, 1);
     finalize(S, 1u, 0);
@@ -1161,12 +1211,21 @@ extern "C" int lfpsqp_large_factor(lfpsqp_ctx *c, const double *x_loc, double *G
     if (S.world > 1) comm_allreduce(S, S.G, (size_t)m * ldm);
     CK(cudaMemcpy2DAsync(G_out, m * 8, S.G, ldm * 8, m * 8, m, cudaMemcpyDeviceToHost, S.stream));
   }
+  S.prefer_pinv = false;
   factorize(c, S);
   if (read_ctrl(c, S)) return LFPSQP_ERR_CUDA;
+  const int lost_rank = S.hctrl->rankflag;
+  if (lost_rank) {   // truncated path: the later project / projcg calls use the pseudo-inverse; L / L^-1 are not defined
+    S.hctrl->rankflag = 0; write_ctrl_fields(S);
+    if (factorize_pinv(c, S, true)) return LFPSQP_ERR_CUDA;
+    if (read_ctrl(c, S)) return LFPSQP_ERR_CUDA;
+    S.rank_cur = (int)S.hctrl->s[14];
+    S.prefer_pinv = false;
+  }
   if (L_out) CK(cudaMemcpy2DAsync(L_out, m * 8, S.G, ldm * 8, m * 8, m, cudaMemcpyDeviceToHost, S.stream));
   if (Linv_out) CK(cudaMemcpy2DAsync(Linv_out, m * 8, S.Linv, ldm * 8, m * 8, m, cudaMemcpyDeviceToHost, S.stream));
   CK(cudaStreamSynchronize(S.stream));
-  if (rank_deficient) *rank_deficient = S.hctrl->rankflag;
+  if (rank_deficient) *rank_deficient = lost_rank ? (m - S.rank_cur > 0 ? m - S.rank_cur : 1) : 0;   // 0, or the rank defect found
   if (gram_ms) { float ms = 0; cudaEventElapsedTime(&ms, S.ev_g0, S.ev_g1); *gram_ms = ms; }
   return LFPSQP_OK;
 }

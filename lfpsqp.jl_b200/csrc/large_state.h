@@ -29,6 +29,12 @@ struct LargeState {
   // explicit-inverse guard: u = G^-1 t loses cond(G) eps, two triangular solves only cond(L) eps.  factorize() bounds cond(G)
   // from above by kappa = trace(G) * lambda_max(G^-1) (power iterations on the explicit inverse); above `inverse_guard` the
   // fused kernel runs the two triangular phases instead (LFPSQP_EXPLICIT_INVERSE=0/1 forces either path: tests)
+  // rank-deficient Jacobians (large_eig.cu): after a failed Cholesky pivot test the solves use the truncated pseudo-inverse
+  // G^+ (held in Ginv) of the eigen-decomposed Gram; rank_cur feeds projcg's iteration cap and the NR / ProjPenalty choice
+  bool pinv_active = false, prefer_pinv = false;
+  int rank_cur = 0;
+  double *eigV = nullptr, *eigT = nullptr, *eigLam = nullptr;
+  unsigned long long *eigScratch = nullptr;    // [32] convergence per sweep | barrier counter | sweeps done
   bool explicit_inverse_ok = true, guard_pending = false;
   double inverse_guard = 1e6, pivot_ratio2 = 1.0;   // pivot_ratio2: the last kappa
   int m = 0, sm_count = 148, world = 1, rank = 0;
@@ -69,6 +75,10 @@ struct LargeState {
 int fused_projcg_chunk(LargeState &S, int iters, int first, double *xs, double *r, double *dc, double *Ad, double *rp, double *gp);
 int fused_pcg(LargeState &S, double *dx, double *r, double *pv, double *z);   // the whole pcg! call as one launch
 void fused_projcg_init(LargeState &S, int device);
+
+// large_eig.cu: eigen-decomposition of the Gram (one-sided Jacobi) -> scaled eigenvectors for the pseudo-inverse
+int large_eig_pinv_factors(LargeState &S, double *G, double *Vt, double *lam, int lower_only, int *sweeps_dev, unsigned long long *conv_dev,
+                           unsigned *bar_dev);
 
 // comm.cu
 void comm_allreduce(LargeState &S, double *buf, size_t count);                  // in-place sum over ranks

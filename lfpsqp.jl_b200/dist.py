@@ -22,7 +22,7 @@ def instance_range(B, world, rank):
 
 def column_range(n, world, rank):
     """Contiguous [col0, col0 + n_loc) column shard with an EVEN n_loc on every rank (128-bit loads need even row
-    lengths); the last rank absorbs the remainder.  Requires n even."""
+    lengths); the remainder pairs go to the first ranks, one each.  Requires n even."""
     if n % 2:
         raise _lib.LFPSQPError("large-n column sharding needs an even n")
     pairs = n // 2

@@ -31,8 +31,10 @@ class LargeProblem:
             raise _lib.LFPSQPError("xl, xu, and x0 must all be the same length")     # optimize.jl:144-148
         self.ctx.check(self.ctx.lib.lfpsqp_large_set_bounds(self.ctx.h, _lib.ptr(xl), _lib.ptr(xu)))
 
-    def solve(self, x0, param=None, history=4096, return_stats=False):
+    def solve(self, x0, param=None, history=None, return_stats=False):
         param = param or LFPSQPParams()
+        if history is None:   # every iterate's objective, as the reference returns (optimize.jl:250, :426)
+            history = int(param.maxiter) + 1
         cp = param.to_c()
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         x = np.empty(self.n_loc); obj = np.full(history, np.nan); olen = np.zeros(1, dtype=np.int64)

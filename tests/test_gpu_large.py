@@ -329,3 +329,50 @@ def test_ill_conditioned_full_solve_vs_oracle(L, oracle, cond):
     assert rec["failures"] == 0, parity.fmt_record(rec)
     if cond <= 1e2:
         assert rec["within_tolerance"] == 1 and status == 0
+
+
+def test_rank_deficient_jacobian_large_mode_vs_oracle(L, oracle):
+    # optimize.jl:297-302 (rank scan), :335-340 (multipliers zeroed beyond the rank), la_helper.jl:36-44 (kgemv! on the leading
+    # `rank` columns) in large-n mode: duplicated constraints at m >= 128 -> the Cholesky pivot test fails -> one-sided Jacobi
+    # eigen-decomposition of the Gram on the device -> truncated pseudo-inverse in every solve.  Oracle: SVD-based.
+    from tests import parity
+    n, m, dup = 1024, 128, 8
+    Q, A, b, xt, w, x0 = L.make_diagquad(n, m, seed=9, cond=50.0)
+    for k in range(dup):                       # rows m-dup.. are copies of rows 0..dup-1 (consistent right-hand sides)
+        Q[m - dup + k] = Q[k]; A[m - dup + k] = A[k]; b[m - dup + k] = b[k]
+    fam = L.families.diagquad(Q, A, b, xt, w)
+    P = L.LargeProblem(fam)
+    # unit level: projector and multipliers against numpy's pseudo-inverse
+    J = Q * x0[None, :] + A
+    fac = P.factor(x0, want=())
+    assert fac["rank_deficient"] == dup
+    v = np.random.default_rng(1).standard_normal(n)
+    pv, lam = P.project(v)
+    Gp = np.linalg.pinv(J @ J.T, rcond=1e-12)
+    assert rel(pv, v - J.T @ (Gp @ (J @ v))) < 1e-10 and rel(lam, Gp @ (J @ v)) < 1e-8
+    assert np.linalg.norm(J @ pv) < 1e-9 * np.linalg.norm(v)
+    assert np.allclose(lam[:dup], lam[m - dup:], rtol=1e-6, atol=1e-10)      # minimum-norm multipliers: copies share equally
+    # full solve vs the oracle
+    x, obj, lmb, info, st, status = P.solve(x0, L.LFPSQPParams(), return_stats=True)
+    assert status & 1                                                         # the truncated path was taken and reported
+    term_dt = [("condition", "<i4"), ("status", "<i4"), ("f_diff", "<f8"), ("step_diff", "<f8"), ("kkt_diff", "<f8"), ("iter", "<i8")]
+
+    def pack(xv, ov, lv, cnd, it, H=20000):
+        t = np.zeros(1, dtype=term_dt); t["condition"] = cnd; t["iter"] = it
+        o = np.full((1, H), np.nan); o[0, :len(ov)] = ov
+        return (xv[None, :], o, np.array([len(ov)]), np.asarray(lv)[None, :], t)
+    runs = {}
+    for vv in ("base", "fma", "seq"):
+        if vv == "base":
+            r = oracle.optimize("diagquad", n, m, 0, x0, fam_params=fam.params)
+        else:
+            with oracle.variant(vv):
+                r = oracle.optimize("diagquad", n, m, 0, x0, fam_params=fam.params)
+        runs[vv] = pack(r[0], r[1], r[2], r[3]["condition"], r[3]["iter"])
+    rec = parity.classify(pack(x, obj, lmb, int(info.condition), info.iter), runs,
+                          "rank-deficient DIAGQUAD n=1024 m=128 (8 duplicated constraints), full solve, large-n mode",
+                          extra={"gpu_iter": int(info.iter), "lam_err_vs_oracle": float(rel(lmb, runs["base"][3][0]))})
+    parity.record(rec)
+    print(parity.fmt_record(rec), "lam err", rel(lmb, runs["base"][3][0]))
+    assert rec["failures"] == 0, parity.fmt_record(rec)
+    assert np.max(np.abs(0.5 * Q @ (x * x) + A @ x - b)) < 1e-6               # feasible to eps_c
