@@ -126,6 +126,14 @@ int lfpsqp_ctx_device_count(lfpsqp_ctx *ctx);
 const char *lfpsqp_last_error(lfpsqp_ctx *ctx);                    /* ctx may be NULL: last error of ctx_create */
 /* run on a caller-owned stream (e.g. torch's current stream) instead of the ctx's own; NULL restores it */
 int lfpsqp_ctx_set_stream(lfpsqp_ctx *ctx, void *cuda_stream);
+/* Stochastic perturbation beta > 0 (src/optimize.jl:264-273) on the device-family paths: the reference adds
+ * beta * max(1 - i / t_beta, 0) * randn!(tmp_n) to d at every outer iteration i.  The caller draws that sequence from ITS OWN RNG
+ * (Julia: randn(N, T) is exactly the stream T successive randn!(tmp_n) calls consume) and hands it over before the solve:
+ * noise[(k * T + i) * N + j] = entry j of the draw of iteration i of instance k; N = working dimension (n + p, doubled when bounds
+ * or d! are present: optimize.jl:172), B = instances of the next lfpsqp_solve_batched* call (large-n: B = 1, N = this rank's
+ * working entries [x-half | y-half]).  Iterations i >= T add no noise (with t_beta > 0, T = t_beta rows cover the whole ramp).
+ * The pointer must stay valid until the solve returns; NULL clears it.  Without it beta > 0 is LFPSQP_ERR_UNSUPPORTED. */
+int lfpsqp_ctx_set_noise(lfpsqp_ctx *ctx, const double *noise, int64_t T, int64_t N, int64_t B);
 /* device time (ms, CUDA events on the launching stream) and launch count of the kernels of the last solve call */
 double lfpsqp_last_kernel_ms(lfpsqp_ctx *ctx);
 int64_t lfpsqp_last_launches(lfpsqp_ctx *ctx);

@@ -34,7 +34,7 @@ EXPORTS = [
     "lfpsqp_comm_unique_id", "lfpsqp_comm_init", "lfpsqp_comm_destroy", "lfpsqp_large_retract", "lfpsqp_large_pcg",
     "lfpsqp_ineq_op", "lfpsqp_large_phase_ms", "lfpsqp_comm_ipc_export", "lfpsqp_comm_ipc_import", "lfpsqp_comm_mode",
     "lfpsqp_large_set_bounds", "lfpsqp_solve_host", "lfpsqp_linesearch", "lfpsqp_aug_hess_vec", "lfpsqp_large_projcg_general",
-    "lfpsqp_ctx_create_multi", "lfpsqp_ctx_device_count",
+    "lfpsqp_ctx_create_multi", "lfpsqp_ctx_device_count", "lfpsqp_ctx_set_noise",
 ]
 
 _lib = None
@@ -59,6 +59,7 @@ def load():
         lib.lfpsqp_ctx_destroy.argtypes = [C.c_void_p]
         lib.lfpsqp_ctx_create_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
         lib.lfpsqp_ctx_device_count.argtypes = [C.c_void_p]
+        lib.lfpsqp_ctx_set_noise.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64]
         lib.lfpsqp_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         P = C.c_void_p
         I = C.c_int64

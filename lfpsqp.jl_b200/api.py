@@ -109,7 +109,7 @@ def _parse(args):
     return f, c, d, dl, du, x0, xl, xu, int(m), int(p), param
 
 
-def optimize_batched(*args, ctx=None, history=64, return_stats=False):
+def optimize_batched(*args, ctx=None, history=64, return_stats=False, noise=None):
     """B independent instances in lockstep on one GPU.  Same positional shapes as `optimize`, with x0 of shape
     (B, n) and per-instance family parameters of shape (B, P).  Returns (x (B,n), obj_values (B,H) NaN-padded,
     obj_len (B,), lambda (B,m+p), term (B,) structured array[, stats])."""
@@ -153,9 +153,16 @@ def optimize_batched(*args, ctx=None, history=64, return_stats=False):
     x = np.empty((B, n)); obj = np.empty((B, H)); olen = np.zeros(B, dtype=np.int64)
     lam = np.zeros((B, m + p)); term = np.zeros(B, dtype=_lib.TERM_DTYPE)
     stats = np.zeros(B, dtype=_lib.STATS_DTYPE) if return_stats else None
+    if noise is not None:   # beta > 0: the caller's randn! rows, (B, T, N_working) (optimize.jl:264-273)
+        noise = np.ascontiguousarray(noise, dtype=np.float64)
+        if noise.ndim != 3 or noise.shape[0] != B:
+            raise _lib.LFPSQPError("noise must have shape (B, T, N_working)")
+        ctx.check(ctx.lib.lfpsqp_ctx_set_noise(ctx.h, _lib.ptr(noise), noise.shape[1], noise.shape[2], B))
     rc = ctx.lib.lfpsqp_solve_batched(ctx.h, fam.id, n, m, p, B, _lib.ptr(fp), stride, _lib.ptr(x0), _lib.ptr(xl),
                                       _lib.ptr(xu), C.cast(C.pointer(cp), C.c_void_p), _lib.ptr(x), _lib.ptr(obj), H,
                                       _lib.ptr(olen), _lib.ptr(lam), _lib.ptr(term), _lib.ptr(stats))
+    if noise is not None:
+        ctx.lib.lfpsqp_ctx_set_noise(ctx.h, None, 0, 0, 0)
     ctx.check(rc)
     if B and int(olen.max()) > H:
         import warnings
@@ -166,7 +173,7 @@ def optimize_batched(*args, ctx=None, history=64, return_stats=False):
     return x, obj, olen, lam, term
 
 
-def optimize(*args, ctx=None, history=None, return_stats=False):
+def optimize(*args, ctx=None, history=None, return_stats=False, noise=None):
     """optimize(f, x0[, param]) / (f, c!, x0, m[, param]) / (f, c!, x0, xl, xu, m[, param]) /
     (f, c!, d!, x0, xl, xu, m, p[, param]) / (f, c!, d!, dl, du, x0, xl, xu, m, p[, param])
     -> (x, obj_values, λ_kkt, term_info), as src/optimize.jl:442."""
@@ -186,7 +193,8 @@ def optimize(*args, ctx=None, history=None, return_stats=False):
     a[idx] = np.asarray(a[idx], dtype=np.float64)[None, :]
     if param is not None:
         a.append(param)
-    out = optimize_batched(*a, ctx=ctx, history=history, return_stats=return_stats)
+    out = optimize_batched(*a, ctx=ctx, history=history, return_stats=return_stats,
+                           noise=None if noise is None else np.asarray(noise, dtype=np.float64)[None])
     x, obj, olen, lam, term = out[:5]
     t = term[0]
     info = TerminationInfo(TerminationCondition(int(t["condition"])), float(t["f_diff"]), float(t["step_diff"]),

@@ -113,6 +113,12 @@ extern "C" int lfpsqp_ctx_set_stream(lfpsqp_ctx *c, void *s) {
   c->stream = s ? (cudaStream_t)s : c->own_stream;
   return LFPSQP_OK;
 }
+extern "C" int lfpsqp_ctx_set_noise(lfpsqp_ctx *c, const double *noise, int64_t T, int64_t N, int64_t B) {
+  if (!c) return LFPSQP_ERR_ARG;
+  if (noise && (T < 1 || N < 1 || B < 1)) return c->fail(LFPSQP_ERR_ARG, "lfpsqp_ctx_set_noise: bad sizes");
+  c->noise_host = noise; c->noise_T = noise ? T : 0; c->noise_N = noise ? N : 0; c->noise_B = noise ? B : 0;
+  return LFPSQP_OK;
+}
 extern "C" double lfpsqp_last_kernel_ms(lfpsqp_ctx *c) { return c ? c->last_ms : -1.0; }
 extern "C" int64_t lfpsqp_last_launches(lfpsqp_ctx *c) { return c ? c->last_launches : 0; }
 
@@ -254,7 +260,12 @@ int check_common(lfpsqp_ctx *c, int family, int64_t n, int64_t m, int64_t p, int
   if (n > (1 << 24)) return c->fail(LFPSQP_ERR_ARG, "n too large");
   if (!fam_valid(family, n, m, p)) return c->fail(LFPSQP_ERR_FAMILY, "family %d does not support n=%lld m=%lld p=%lld", family,
                                                   (long long)n, (long long)m, (long long)p);
-  if (prm->beta > 0) return c->fail(LFPSQP_ERR_UNSUPPORTED, "beta>0 (stochastic perturbation, optimize.jl:264-273) needs Julia's RNG stream");
+  if (prm->beta > 0) {
+    if (!c->noise_host) return c->fail(LFPSQP_ERR_UNSUPPORTED, "beta>0 (stochastic perturbation, optimize.jl:264-273) needs the caller's noise "
+                                                               "sequence: lfpsqp_ctx_set_noise (device families) or the randn callback (lfpsqp_solve_host)");
+    if (c->noise_B != B || c->noise_T < 1) return c->fail(LFPSQP_ERR_ARG, "lfpsqp_ctx_set_noise: noise was supplied for %lld instances, the batch has %lld",
+                                                           (long long)c->noise_B, (long long)B);
+  }
   return LFPSQP_OK;
 }
 
@@ -275,6 +286,10 @@ static int prepare_batched(lfpsqp_ctx *c, int family, int64_t n, int64_t m, int6
   if (ineq < 0) return c->fail(ineq, "xl, xu, and x0 must all be the same length (both or neither may be NULL)");
   memset(&A, 0, sizeof(A));
   A.family = family; A.n = (int)n; A.m = (int)m; A.p = (int)p; A.ineq = ineq; A.B = B; A.prm = *prm; A.H = H;
+  if (prm->beta > 0) {
+    const int64_t Nw = (ineq ? 2 : 1) * (n + p);      // the working dimension the reference draws randn! for (optimize.jl:172, :265)
+    if (c->noise_N != Nw) return c->fail(LFPSQP_ERR_ARG, "lfpsqp_ctx_set_noise: rows of %lld entries, the working dimension is %lld", (long long)c->noise_N, (long long)Nw);
+  }
   if (ineq && B > 0) {
     double *dbnd = (double *)c->arena(0, bnd.size() * 8);
     if (!dbnd) return c->fail(LFPSQP_ERR_NOMEM, "device allocation failed");
@@ -298,6 +313,13 @@ extern "C" int lfpsqp_solve_batched_dev(lfpsqp_ctx *c, int family, int64_t n, in
   A.fam_params = fam_params_dev; A.fam_stride = fam_stride; A.x0 = x0_dev;
   A.x_out = x_out_dev; A.obj_hist = obj_hist_dev; A.obj_len = obj_len_dev; A.lambda = lambda_dev;
   A.term = term_dev; A.stats = stats_dev;
+  if (prm->beta > 0) {
+    const size_t nb = (size_t)c->noise_B * c->noise_T * c->noise_N * 8;
+    double *d_noise = (double *)c->arena(9, nb);
+    if (!d_noise) return c->fail(LFPSQP_ERR_NOMEM, "device allocation failed");
+    cudaMemcpyAsync(d_noise, c->noise_host, nb, cudaMemcpyHostToDevice, c->stream);
+    A.noise = d_noise; A.noise_T = c->noise_T;
+  }
   cudaMemsetAsync(obj_hist_dev, 0xff, (size_t)H * B * 8, c->stream);   // NaN-fill the unused tail of the history, as the host entry does
   rc = dispatch_batched(c, A);
   if (rc) return rc;
@@ -331,7 +353,9 @@ extern "C" int lfpsqp_solve_batched(lfpsqp_ctx *c, int family, int64_t n, int64_
   int64_t *d_len = (int64_t *)c->arena(5, (size_t)B * 8);
   lfpsqp_term *d_term = (lfpsqp_term *)c->arena(7, (size_t)B * sizeof(lfpsqp_term));
   lfpsqp_stats *d_stats = stats ? (lfpsqp_stats *)c->arena(8, (size_t)B * sizeof(lfpsqp_stats)) : nullptr;
-  if (!d_par || !d_x0 || !d_x || !d_obj || !d_lam || !d_len || !d_term || (stats && !d_stats))
+  const size_t noise_row = (prm->beta > 0) ? (size_t)c->noise_T * c->noise_N : 0;    // doubles per instance
+  double *d_noise = noise_row ? (double *)c->arena(9, noise_row * B * 8) : nullptr;
+  if (!d_par || !d_x0 || !d_x || !d_obj || !d_lam || !d_len || !d_term || (stats && !d_stats) || (noise_row && !d_noise))
     return c->fail(LFPSQP_ERR_NOMEM, "device allocation failed");
   // chunking: keep every chunk big enough to fill the GPU several times over
   int nchunk = 1;
@@ -354,6 +378,10 @@ extern "C" int lfpsqp_solve_batched(lfpsqp_ctx *c, int family, int64_t n, int64_
     cudaMemsetAsync(d_obj + lo * H, 0xff, (size_t)H * nb * 8, s);  // NaN-fill the unused tail of the history
     BatchedArgs A = A0;
     A.B = nb;
+    if (noise_row) {
+      cudaMemcpyAsync(d_noise + lo * noise_row, c->noise_host + lo * noise_row, noise_row * nb * 8, cudaMemcpyHostToDevice, s);
+      A.noise = d_noise + lo * noise_row; A.noise_T = c->noise_T;
+    }
     A.fam_params = npar ? (fam_stride ? d_par + lo * fam_stride : d_par) : nullptr; A.fam_stride = fam_stride;
     A.x0 = d_x0 + lo * n; A.x_out = d_x + lo * n; A.obj_hist = d_obj + lo * H; A.obj_len = d_len + lo;
     A.lambda = d_lam + lo * ME; A.term = d_term + lo; A.stats = d_stats ? d_stats + lo : nullptr;

@@ -779,6 +779,16 @@ struct RegSolver {
           d.x[s] = -1.0 * gs;
           if (INEQ) d.y[s] = -0.0;
         }
+        if (A.noise) {                                                           // :264-273, caller-supplied noise rows
+          const double nc = noise_coef(prm, it, A.noise_T);
+          if (nc != 0.0) {
+            const int Nw = INEQ ? 2 * NA : NA;
+            const double *nz = A.noise + ((int64_t)k * A.noise_T + it) * Nw;
+            LF_UNROLL for (int s = 0; s < NPL; s++) {
+              if (idx(s) < NA) { d.x[s] += nc * nz[idx(s)]; if (INEQ) d.y[s] += nc * nz[NA + idx(s)]; }
+            }
+          }
+        }
         if (INEQ) inequality_gradient(x);
         if (ME > 0) {
           jac_aux(cval, x);

@@ -39,7 +39,15 @@ __global__ void __launch_bounds__(128) batched_tiny_kernel(const BatchedArgs A) 
     Fam::grad(g, fc, gr, x);                                               // optimize.jl:259
     kkt_diff = 0.0;
 #pragma unroll
-    for (int i = 0; i < NT; i++) { d[i] = -1.0 * gr[i]; kkt_diff = pmax(fabs(d[i]), kkt_diff); }   // :262, :320
+    for (int i = 0; i < NT; i++) d[i] = -1.0 * gr[i];                                              // :262
+    if (A.noise) {                                                                                   // :264-273
+      const double nc = noise_coef(prm, it, A.noise_T);
+      if (nc != 0.0) { const double *nz = A.noise + ((int64_t)k * A.noise_T + it) * NT;
+#pragma unroll
+        for (int i = 0; i < NT; i++) d[i] += nc * nz[i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < NT; i++) kkt_diff = pmax(fabs(d[i]), kkt_diff);                            // :320
     if (f_diff <= prm.eps_f) { cond = LFPSQP_F_TOL; break; }               // :347-359
     else if (step_diff <= prm.eps_x) { cond = LFPSQP_X_TOL; break; }
     else if (it >= prm.maxiter) { cond = LFPSQP_MAX_ITER; break; }

@@ -734,6 +734,10 @@ struct Solver {
     while (true) {
       grad_aux(gr, x);                                                     // :259
       for (int i = g.lane; i < N; i += G::SIZE) d[i] = -1.0 * gr[i];       // :262
+      if (A.noise) {                                                       // :264-273, caller-supplied noise rows
+        const double nc = noise_coef(prm, it, A.noise_T);
+        if (nc != 0.0) { const double *nz = A.noise + ((int64_t)k * A.noise_T + it) * N; for (int i = g.lane; i < N; i += G::SIZE) d[i] += nc * nz[i]; }
+      }
       g.sync();
       if (ineq) inequality_gradient(x);                                    // :277
       if (ME > 0) {

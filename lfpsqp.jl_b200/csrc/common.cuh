@@ -56,6 +56,15 @@ struct BatchedArgs {
   lfpsqp_params prm;
   double *x_out; double *obj_hist; int64_t H; int64_t *obj_len; double *lambda; lfpsqp_term *term; lfpsqp_stats *stats;
   unsigned long long *work_counter;  // persistent-CTA work queue
+  // stochastic perturbation of optimize.jl:264-273 with a caller-supplied noise sequence (lfpsqp_ctx_set_noise): instance k,
+  // outer iteration i < noise_T uses the N working entries at noise + (k * noise_T + i) * N ; nullptr when beta == 0
+  const double *noise; int64_t noise_T;
 };
+
+// coefficient of the noise term at outer iteration i (optimize.jl:267-271); 0 beyond the supplied rows
+LFPSQP_DEV double noise_coef(const lfpsqp_params &prm, int64_t i, int64_t T) {
+  if (!(prm.beta > 0.0) || i >= T) return 0.0;
+  return prm.t_beta > 0 ? prm.beta * fmax(1.0 - (double)i / (double)prm.t_beta, 0.0) : prm.beta;
+}
 
 }  // namespace lfpsqp

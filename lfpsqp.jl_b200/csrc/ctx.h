@@ -36,6 +36,8 @@ struct lfpsqp_ctx {
   // multi-GPU context (lfpsqp_ctx_create_multi): one child ctx per device; batched solves shard contiguous instance ranges
   // over the children from one host call (one host thread per device, no collective).  Empty for a single-GPU ctx.
   std::vector<lfpsqp_ctx *> children;
+  // caller-supplied noise of the next device-family solve (lfpsqp_ctx_set_noise): host pointer owned by the caller
+  const double *noise_host = nullptr; int64_t noise_T = 0, noise_N = 0, noise_B = 0;
   std::vector<double> bnd_host;   // host copy of the bound table of the current batched call: [kind | q | r | s | t] x NA
 
   int fail(int code, const char *fmt, ...);

@@ -345,16 +345,33 @@ static int factorize(lfpsqp_ctx *c, LargeState &S) {
   constexpr int NB = 64;
   const size_t psm = 2 * NB * (NB + 1) * sizeof(double);
   int nblk = (m + NB - 1) / NB;
+  // Right-looking blocked Cholesky with LOOK-AHEAD: the single-CTA factorisation of diagonal block b+1 (latency-bound, ~50 us)
+  // runs on a second stream while the main stream applies the rank-NB update of block b to the rest of the trailing matrix.
+  // Per block: potf2(b) -> L21 = A21 D' -> [panel part of the update: the nb2 columns of block b+1] -> event -> potf2(b+1) on
+  // the side stream || [remaining trailing update] on the main stream.
+  if (!S.side_stream) {
+    cudaStreamCreateWithFlags(&S.side_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&S.ev_panel, cudaEventDisableTiming); cudaEventCreateWithFlags(&S.ev_potf, cudaEventDisableTiming);
+  }
+  cudaStream_t main_s = S.stream, side_s = S.side_stream ? S.side_stream : S.stream;
+  potf2_inv_kernel<NB><<<1, 256, psm, main_s>>>(S.G, ldm, std::min(NB, m), S.Dblk, S.thresh, &S.ctrl->rankflag);
+  S.launches++;
   for (int b = 0; b < nblk; b++) {
     int j0 = b * NB, nb = std::min(NB, m - j0), rem = m - j0 - nb;
-    double *Ajj = S.G + (int64_t)j0 * ldm + j0, *Db = S.Dblk + (size_t)b * NB * NB;
-    potf2_inv_kernel<NB><<<1, 256, psm, S.stream>>>(Ajj, ldm, nb, Db, S.thresh, &S.ctrl->rankflag);
+    double *Db = S.Dblk + (size_t)b * NB * NB;
+    if (rem <= 0) break;
+    double *A21 = S.G + (int64_t)(j0 + nb) * ldm + j0;
+    double *A22 = S.G + (int64_t)(j0 + nb) * ldm + (j0 + nb);
+    gemm_nt(S, rem, nb, nb, A21, ldm, Db, NB, A21, ldm, GEMM_ASSIGN, 0);                         // L21 = A21 D'
+    const int nb2 = std::min(NB, rem), rem2 = rem - nb2;
+    gemm_nt(S, rem, nb2, nb, A21, ldm, A21, ldm, A22, ldm, GEMM_SUB, 0);                         // panel of block b+1: A22[:, 0:nb2] -= L21 L21[0:nb2]'
+    if (side_s != main_s) { cudaEventRecord(S.ev_panel, main_s); cudaStreamWaitEvent(side_s, S.ev_panel, 0); }
+    potf2_inv_kernel<NB><<<1, 256, psm, side_s>>>(A22, ldm, nb2, S.Dblk + (size_t)(b + 1) * NB * NB, S.thresh, &S.ctrl->rankflag);
     S.launches++;
-    if (rem > 0) {
-      double *A21 = S.G + (int64_t)(j0 + nb) * ldm + j0;
-      gemm_nt(S, rem, nb, nb, A21, ldm, Db, NB, A21, ldm, GEMM_ASSIGN, 0);                       // L21 = A21 D'
-      gemm_nt(S, rem, rem, nb, A21, ldm, A21, ldm, S.G + (int64_t)(j0 + nb) * ldm + (j0 + nb), ldm, GEMM_SUB, 1);  // A22 -= L21 L21'
-    }
+    if (side_s != main_s) cudaEventRecord(S.ev_potf, side_s);
+    if (rem2 > 0)                                                                                // the rest of A22 -= L21 L21' (lower)
+      gemm_nt(S, rem2, rem2, nb, A21 + (int64_t)nb2 * ldm, ldm, A21 + (int64_t)nb2 * ldm, ldm, A22 + (int64_t)nb2 * ldm + nb2, ldm, GEMM_SUB, 1);
+    if (side_s != main_s) cudaStreamWaitEvent(main_s, S.ev_potf, 0);
   }
   // XT = L^-T (upper triangular, row-major), block row by block row; Linv = XT'
   cudaMemsetAsync(S.XT, 0, (size_t)m * ldm * sizeof(double), S.stream);
@@ -837,13 +854,18 @@ static int solve(lfpsqp_ctx *c, LargeState &S, const double *x0_host, double *x_
     fam_grad(S, g, x);                                                                  // :259
     vec(S, nv, [=] __device__(int64_t i, double *) { d[i] = -1.0 * g[i]; });             // :262
     S.launches++;
-    if (prm.beta > 0) {                                                                 // :264-273, randn! from the caller's RNG
+    if (prm.beta > 0 && S.cb.randn) {                                                   // :264-273, randn! from the caller's RNG
       if (S.cb.randn(S.cb.user, S.hw, nv)) S.cb_err = 1;
       double *noise = S.w0;
       CK(cudaMemcpyAsync(noise, S.hw, nv * sizeof(double), cudaMemcpyHostToDevice, S.stream));
       const double coef = prm.t_beta > 0 ? prm.beta * fmax(1.0 - (double)it / (double)prm.t_beta, 0.0) : prm.beta;
       vec(S, nv, [=] __device__(int64_t i, double *) { d[i] += coef * noise[i]; });
       CK(cudaStreamSynchronize(S.stream));   // S.hw is reused by the next callback
+    } else if (prm.beta > 0 && it < S.noise_T) {                                        // device families: the caller's noise rows
+      const double coef = prm.t_beta > 0 ? prm.beta * fmax(1.0 - (double)it / (double)prm.t_beta, 0.0) : prm.beta;
+      const double *noise = S.noise_dev + (size_t)it * nv;
+      vec(S, nv, [=] __device__(int64_t i, double *) { d[i] += coef * noise[i]; });
+      S.launches++;
     }
     if (ineq) ineq_gradient(S, x);                                                      // :277
     if (m > 0 || ineq) {
@@ -969,6 +991,9 @@ void lfpsqp_large_release(lfpsqp_ctx *c) {
   for (void *p : S->owned) cudaFree(p);
   if (S->hctrl) cudaFreeHost(S->hctrl);
   for (double *p : {S->hx, S->hv, S->hw, S->hlam, S->hc, S->hJ}) if (p) cudaFreeHost(p);
+  if (S->side_stream) cudaStreamDestroy(S->side_stream);
+  if (S->ev_panel) cudaEventDestroy(S->ev_panel);
+  if (S->ev_potf) cudaEventDestroy(S->ev_potf);
   if (S->ev_g0) cudaEventDestroy(S->ev_g0);
   if (S->ev_g1) cudaEventDestroy(S->ev_g1);
   comm_release(*S);
@@ -1099,8 +1124,16 @@ static int need_large(lfpsqp_ctx *c) {
 }
 static int prep_params(lfpsqp_ctx *c, LargeState &S, const lfpsqp_params *prm) {
   if (!prm) return c->fail(LFPSQP_ERR_ARG, "params is NULL");
-  if (prm->beta > 0 && !S.cb.randn)
-    return c->fail(LFPSQP_ERR_UNSUPPORTED, "beta>0 needs the randn host callback (LFPSQP_FAM_HOST): the noise must come from the caller's RNG stream");
+  if (prm->beta > 0 && !S.cb.randn) {
+    if (!c->noise_host) return c->fail(LFPSQP_ERR_UNSUPPORTED, "beta>0 needs the caller's noise: lfpsqp_ctx_set_noise (device families) or the randn host callback (LFPSQP_FAM_HOST)");
+    if (c->noise_N != S.nv || c->noise_B != 1) return c->fail(LFPSQP_ERR_ARG, "lfpsqp_ctx_set_noise: large-n mode needs B = 1 and rows of %lld entries (this rank's working entries)", (long long)S.nv);
+    if (S.noise_cap < (size_t)c->noise_T * S.nv) {
+      if (!dalloc(S, &S.noise_dev, (size_t)c->noise_T * S.nv)) return c->fail(LFPSQP_ERR_NOMEM, "noise buffer allocation failed");
+      S.noise_cap = (size_t)c->noise_T * S.nv;
+    }
+    CK(cudaMemcpyAsync(S.noise_dev, c->noise_host, (size_t)c->noise_T * S.nv * 8, cudaMemcpyHostToDevice, S.stream));
+    S.noise_T = c->noise_T;
+  } else S.noise_T = 0;
   S.prm = *prm;
   if (prm->linesearch != 0 && !prm->disable_linesearch && !S.ex[0]) {
     for (int i = 0; i < 4; i++) if (!dalloc(S, &S.ex[i], 2 * (size_t)S.n_loc + 2)) return c->fail(LFPSQP_ERR_NOMEM, "exact line search workspace allocation failed");

@@ -35,6 +35,7 @@ struct LargeState {
   int rank_cur = 0;
   double *eigV = nullptr, *eigT = nullptr, *eigLam = nullptr;
   unsigned long long *eigScratch = nullptr;    // [32] convergence per sweep | barrier counter | sweeps done
+  double *noise_dev = nullptr; size_t noise_cap = 0; int64_t noise_T = 0;   // caller-supplied noise rows (lfpsqp_ctx_set_noise), beta > 0
   bool explicit_inverse_ok = true, guard_pending = false;
   double inverse_guard = 1e6, pivot_ratio2 = 1.0;   // pivot_ratio2: the last kappa
   int m = 0, sm_count = 148, world = 1, rank = 0;
@@ -59,6 +60,8 @@ struct LargeState {
   lfpsqp::LargeCtrl *ctrl = nullptr, *hctrl = nullptr;
   int vgrid = 1, np_loop = 1, np_loop_raw = 1, cg_chunk = 2, pcg_chunk = 2;
   cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr;
+  cudaStream_t side_stream = nullptr;                  // look-ahead of the blocked Cholesky (large.cu::factorize)
+  cudaEvent_t ev_panel = nullptr, ev_potf = nullptr;
   std::vector<void *> owned;
   // counters
   int64_t collectives = 0, launches = 0, projcg_iters = 0, projcg_negcurv = 0, armijo_trials = 0, retract_outer = 0, retract_pcg = 0,

@@ -43,6 +43,8 @@ int solve_batched_multi(lfpsqp_ctx *c, int family, int64_t n, int64_t m, int64_t
     const int64_t lo = g * base + std::min<int64_t>(g, rem), nb = base + (g < rem ? 1 : 0);
     lfpsqp_ctx *ch = c->children[g];
     if (nb == 0) { rcs[g] = 0; ch->last_ms = 0; ch->last_launches = 0; return; }
+    if (c->noise_host) { ch->noise_host = c->noise_host + lo * c->noise_T * c->noise_N; ch->noise_T = c->noise_T; ch->noise_N = c->noise_N; ch->noise_B = nb; }
+    else { ch->noise_host = nullptr; ch->noise_T = ch->noise_N = ch->noise_B = 0; }
     rcs[g] = lfpsqp_solve_batched(ch, family, n, m, p, nb, fam_params ? fam_params + (fam_stride ? lo * fam_stride : 0) : nullptr, fam_stride,
                                   x0 ? x0 + lo * n : nullptr, xl, xu, prm, x_out ? x_out + lo * n : nullptr, obj_hist ? obj_hist + lo * H : nullptr, H,
                                   obj_len ? obj_len + lo : nullptr, lambda ? lambda + lo * ME : nullptr, term ? term + lo : nullptr,

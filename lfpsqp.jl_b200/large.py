@@ -31,8 +31,12 @@ class LargeProblem:
             raise _lib.LFPSQPError("xl, xu, and x0 must all be the same length")     # optimize.jl:144-148
         self.ctx.check(self.ctx.lib.lfpsqp_large_set_bounds(self.ctx.h, _lib.ptr(xl), _lib.ptr(xu)))
 
-    def solve(self, x0, param=None, history=None, return_stats=False):
+    def solve(self, x0, param=None, history=None, return_stats=False, noise=None):
+        """noise (beta > 0): (T, N_working_local) rows of the caller's randn! sequence (optimize.jl:264-273)"""
         param = param or LFPSQPParams()
+        if noise is not None:
+            noise = np.ascontiguousarray(noise, dtype=np.float64)
+            self.ctx.check(self.ctx.lib.lfpsqp_ctx_set_noise(self.ctx.h, _lib.ptr(noise), noise.shape[0], noise.shape[1], 1))
         if history is None:   # every iterate's objective, as the reference returns (optimize.jl:250, :426)
             history = int(param.maxiter) + 1
         cp = param.to_c()
@@ -42,6 +46,8 @@ class LargeProblem:
         self.ctx.check(self.ctx.lib.lfpsqp_large_solve(self.ctx.h, _lib.ptr(x0), C.cast(C.pointer(cp), C.c_void_p), _lib.ptr(x),
                                                        _lib.ptr(obj), history, _lib.ptr(olen), _lib.ptr(lam), _lib.ptr(term),
                                                        _lib.ptr(stats)))
+        if noise is not None:
+            self.ctx.lib.lfpsqp_ctx_set_noise(self.ctx.h, None, 0, 0, 0)
         t = term[0]
         info = TerminationInfo(TerminationCondition(int(t["condition"])), float(t["f_diff"]), float(t["step_diff"]),
                                float(t["kkt_diff"]), int(t["iter"]))

@@ -24,6 +24,11 @@ typedef std::vector<double> vec;
 static const double INF = std::numeric_limits<double>::infinity();
 static const double QNAN = std::numeric_limits<double>::quiet_NaN();
 
+/* caller-supplied noise rows for beta > 0 (optimize.jl:264-273): the reference draws randn!(tmp_n) from Julia's global RNG; here
+   the test supplies the same numbers to the oracle and to the device path.  Row i of the current instance at t_noise + i*N. */
+static const double *g_noise = nullptr; static int64_t g_noise_T = 0, g_noise_stride = 0;
+static thread_local const double *t_noise = nullptr;
+extern "C" void orc_set_noise(const double *noise, int64_t T, int64_t stride_per_instance) { g_noise = noise; g_noise_T = T; g_noise_stride = stride_per_instance; t_noise = noise; }
 static thread_local double g_flops = 0.0;
 static thread_local orc_stats *g_stats = nullptr;
 
@@ -789,7 +794,7 @@ static LsOut exact_linesearch(double *xnew, const double *x, int64_t n, int64_t 
 static int core(Problem &P, const double *x0, const double *xl, const double *xu, const orc_params &prm, double *x_out,
                 double *obj_hist, int64_t obj_cap, int64_t *obj_len, double *lambda, orc_term *term) {
   int64_t n = P.n, m = P.m;
-  if (prm.beta > 0) return -10; /* stochastic perturbation (optimize.jl:264-273) needs Julia's RNG stream: unsupported */
+  if (prm.beta > 0 && !t_noise) return -10; /* stochastic perturbation (optimize.jl:264-273): needs the noise rows (orc_set_noise) */
   bool ineq;
   if (!xl && !xu) ineq = false;                               /* :151 */
   else {
@@ -833,6 +838,11 @@ static int core(Problem &P, const double *x0, const double *xl, const double *xu
   while (true) {
     P.grad(g.data(), x.data());                                 /* :259 (g[n+1:] stays 0) */
     for (int64_t k = 0; k < N; k++) d[k] = -1.0 * g[k];
+    if (prm.beta > 0 && i < g_noise_T) {                        /* :264-273 with the supplied randn! rows */
+      const double coef = prm.t_beta > 0 ? prm.beta * std::max(1.0 - (double)i / (double)prm.t_beta, 0.0) : prm.beta;
+      const double *nz = t_noise + i * N;
+      for (int64_t k = 0; k < N; k++) d[k] += coef * nz[k];
+    }
     if (ineq) inequality_gradient(de, x.data(), idata);         /* :277 */
     int64_t rank = m;
     if (m > 0) {
@@ -950,6 +960,7 @@ extern "C" int orc_optimize_batched(int family, const double *fam_params, int64_
       int64_t k0 = next.fetch_add(64);
       if (k0 >= B) break;
       for (int64_t k = k0; k < std::min(B, k0 + 64); k++) {
+        t_noise = g_noise ? g_noise + k * g_noise_stride : nullptr;
         int rc = orc_optimize(family, fam_params ? fam_params + k * fam_stride : nullptr, n, m, p, x0 + k * n, xl, xu, prm,
                               x_out + k * n, obj_hist + k * H, H, obj_len + k, lambda + k * (m + p), term + k,
                               stats ? stats + k : nullptr);

@@ -65,6 +65,8 @@ enum {
 };
 
 void orc_default_params(orc_params *p);
+/* noise rows for beta > 0 (optimize.jl:264-273): row i (N working entries) of instance k at noise + k*stride + i*N; NULL clears */
+void orc_set_noise(const double *noise, int64_t T, int64_t stride_per_instance);
 /* dlopen the LAPACK provider (scipy's bundled OpenBLAS) and bind dgesvd. returns 0 on success */
 int orc_set_lapack(const char *libpath);
 

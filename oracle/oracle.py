@@ -101,6 +101,26 @@ class variant:
         _lib = self.prev
 
 
+_noise_keep = None
+
+
+def set_noise(noise):
+    """noise: None, or array (B, T, N) / (T, N) of the randn! rows for beta > 0 (optimize.jl:264-273)."""
+    global _noise_keep
+    if noise is None:
+        _noise_keep = None
+        for L in list(_libs.values()) or [lib()]:
+            L.orc_set_noise(None, C.c_int64(0), C.c_int64(0))
+        return
+    a = np.ascontiguousarray(noise, dtype=np.float64)
+    if a.ndim == 2:
+        a = a[None]
+    _noise_keep = a
+    lib()
+    for L in _libs.values():
+        L.orc_set_noise(_dp(a), C.c_int64(a.shape[1]), C.c_int64(a.shape[1] * a.shape[2]))
+
+
 def default_params(**kw):
     p = Params()
     lib().orc_default_params(C.byref(p))

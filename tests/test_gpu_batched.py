@@ -277,3 +277,53 @@ def test_multi_device_context_shards_instances(L, oracle):
         mc.close()
     with pytest.raises(L.LFPSQPError):
         L.MultiContext([0, 0])               # each device once
+
+
+def test_beta_noise_on_device_family_paths_vs_oracle(L, oracle):
+    # optimize.jl:264-273 (d += beta max(1 - i/t_beta, 0) randn!(tmp_n)) on the DEVICE-FAMILY paths: the caller supplies the
+    # randn! rows (lfpsqp_ctx_set_noise); the oracle gets the same rows.  All three batched kernels + the large-n engine.
+    rng = np.random.default_rng(77)
+    T = 6
+    prm = L.LFPSQPParams(beta=5e-2, t_beta=T)
+    oprm = lambda: oracle.default_params(beta=5e-2, t_beta=T)
+    try:
+        # thread-per-instance kernel (Rosenbrock)
+        B = 256
+        x0 = rng.uniform(-2, 2, (B, 2)); nz = rng.standard_normal((B, T, 2))
+        gpu = L.optimize_batched(L.families.rosenbrock().f, x0, prm, history=128, noise=nz)
+        oracle.set_noise(nz)
+        orc = oracle.optimize_batched("rosenbrock", 2, 0, 0, x0, params=oprm(), H=128, nthreads=8)
+        noiseless = oracle.optimize_batched("rosenbrock", 2, 0, 0, x0, H=128, nthreads=8)
+        assert (np.linalg.norm(orc[0] - noiseless[0], axis=1) > 1e-9).mean() > 0.5 or (orc[4]["iter"] != noiseless[4]["iter"]).mean() > 0.3   # the noise matters
+        _require(compare_batch(gpu, orc, 2, "rosenbrock beta>0"), 0.97)
+        # register kernel (README inequality: working dimension 2 (n + p))
+        B, n = 128, 50
+        co = rng.standard_normal((B, n)); inf = np.inf * np.ones(n); nz = rng.standard_normal((B, T, 2 * (n + 1)))
+        fam = L.families.readme_inequality(co)
+        gpu = L.optimize_batched(fam.f, None, fam.d, np.zeros((B, n)), -inf, inf, 0, 1, prm, noise=nz)
+        oracle.set_noise(nz)
+        orc = oracle.optimize_batched("readme_ineq", n, 0, 1, np.zeros((B, n)), xl=-inf, xu=inf, fam_params=co, fam_stride=n, params=oprm(), nthreads=8)
+        _require(compare_batch(gpu, orc, n, "readme_ineq beta>0"), 0.97)
+        # shared-memory warp kernel (sin system, equality constraints)
+        B, n, m = 64, 24, 6
+        t = rng.standard_normal((B, n)); nz = rng.standard_normal((B, T, n))
+        fam = L.families.sin_system(n, m, t)
+        gpu = L.optimize_batched(fam.f, fam.c, np.zeros((B, n)), m, prm, noise=nz)
+        oracle.set_noise(nz)
+        orc = oracle.optimize_batched("sin", n, m, 0, np.zeros((B, n)), fam_params=t, fam_stride=n, params=oprm(), nthreads=8)
+        _require(compare_batch(gpu, orc, n, "sin beta>0"), 0.95)
+        # large-n engine (DIAGQUAD)
+        n, m = 512, 32
+        Q, A, b, xt, w, x0 = L.make_diagquad(n, m, seed=3, cond=50.0)
+        fam = L.families.diagquad(Q, A, b, xt, w)
+        nz = rng.standard_normal((T, n))
+        x, obj, lam, info = L.LargeProblem(fam).solve(x0, prm, noise=nz)
+        oracle.set_noise(nz)
+        ox, oobj, olam, ot, _ = oracle.optimize("diagquad", n, m, 0, x0, fam_params=fam.params, params=oprm())
+        assert int(info.condition) == ot["condition"] and abs(info.iter - ot["iter"]) <= 1
+        assert np.linalg.norm(x - ox) <= 1e-8 * np.linalg.norm(ox) and abs(obj[-1] - oobj[-1]) <= 1e-10 * abs(oobj[-1])
+    finally:
+        oracle.set_noise(None)
+    # without the noise rows beta > 0 is refused (no silent deterministic run)
+    with pytest.raises(L.LFPSQPError, match="beta>0"):
+        L.optimize_batched(L.families.rosenbrock().f, np.zeros((4, 2)), prm)
