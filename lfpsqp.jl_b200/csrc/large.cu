@@ -143,10 +143,19 @@ static void gram_solve(LargeState &S, const double *t, double *u, double *u_copy
 }
 
 // ------------------------------------------------------------------ family dispatch (device callbacks, whole-GPU kernels)
-static void thomson_grid(LargeState &S, int np, dim3 &grid) {
-  int ib = (np + 255) / 256;
+static void thomson_grid(LargeState &S, int npl, dim3 &grid) {   // npl = owned points
+  int ib = (npl + 255) / 256;
   int js = std::max(1, std::min(16, (2 * S.sm_count) / ib));
   grid = dim3(ib, js);
+}
+// Thomson's callbacks need the coordinates of ALL points: all-gather of this rank's entries of an n-vector,
+// done as an all-reduce of the zero-padded vector (98 KB at N = 4096).  Single GPU: the vector itself.
+static const double *thomson_gather(LargeState &S, const double *v_loc, double *full) {
+  if (S.world <= 1) return v_loc;
+  cudaMemsetAsync(full, 0, (size_t)S.n * sizeof(double), S.stream);
+  cudaMemcpyAsync(full + S.col0, v_loc, (size_t)S.n_loc * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);
+  comm_allreduce(S, full, (size_t)S.n);
+  return full;
 }
 // ---- host-callback family: the first n entries of a device vector -> pinned S.hx (blocking; also orders every earlier
 // H2D copy out of the pinned staging buffers before the callback may overwrite them)
@@ -167,9 +176,10 @@ static void fam_f(LargeState &S, const double *x) {  // -> gpart slot 0 (sum); c
     const double *xt = S.p_xt, *w = S.p_w;
     vec(S, S.n_loc, [=] __device__(int64_t j, double *acc) { double t = x[j] - xt[j]; acc[0] += 0.5 * w[j] * t * t; }, 0, 1);
   } else {
-    int np = (int)(S.n / 3);
-    dim3 grid; thomson_grid(S, np, grid);
-    thomson_pair_kernel<0><<<grid, 256, 0, S.stream>>>(np, x, nullptr, nullptr, S.gpart, 0, S.ctrl, 0);
+    const int np = (int)(S.n / 3), npl = (int)(S.n_loc / 3), i0 = (int)(S.col0 / 3);
+    const double *xf = thomson_gather(S, x, S.xfull);
+    dim3 grid; thomson_grid(S, npl, grid);
+    thomson_pair_kernel<0><<<grid, 256, 0, S.stream>>>(np, i0, npl, xf, nullptr, nullptr, S.gpart, 0, S.ctrl, 0);
     // the pair kernel wrote grid.x*grid.y partials: fold them into the vgrid partials finalize() expects
     collapse_partials_kernel<<<1, 256, 0, S.stream>>>(S.gpart, grid.x * grid.y, S.vgrid);
   }
@@ -184,10 +194,11 @@ static void fam_grad(LargeState &S, double *g, const double *x) {
     const double *xt = S.p_xt, *w = S.p_w;
     vec(S, S.n_loc, [=] __device__(int64_t j, double *) { g[j] = w[j] * (x[j] - xt[j]); });
   } else {
-    int np = (int)(S.n / 3);
-    dim3 grid; thomson_grid(S, np, grid);
-    thomson_pair_kernel<1><<<grid, 256, 0, S.stream>>>(np, x, nullptr, S.pairws, nullptr, 0, S.ctrl, 0);
-    thomson_reduce_kernel<1><<<(3 * np + 255) / 256, 256, 0, S.stream>>>(np, grid.y, S.pairws, nullptr, nullptr, g, nullptr, 0, S.ctrl, 0);
+    const int np = (int)(S.n / 3), npl = (int)(S.n_loc / 3), i0 = (int)(S.col0 / 3);
+    const double *xf = thomson_gather(S, x, S.xfull);
+    dim3 grid; thomson_grid(S, npl, grid);
+    thomson_pair_kernel<1><<<grid, 256, 0, S.stream>>>(np, i0, npl, xf, nullptr, S.pairws, nullptr, 0, S.ctrl, 0);
+    thomson_reduce_kernel<1><<<(3 * npl + 255) / 256, 256, 0, S.stream>>>(npl, grid.y, S.pairws, nullptr, nullptr, g, nullptr, 0, S.ctrl, 0);
     S.launches++;
   }
   S.launches++;
@@ -214,13 +225,18 @@ static void fam_c_jac(LargeState &S, double *Jout, double *cval, const double *x
     S.launches += 2;
   } else {
     if (Jout) cudaMemsetAsync(Jout, 0, (size_t)m * S.ldj * sizeof(double), S.stream);  // dense-treated, as the reference
-    thomson_c_kernel<<<(m + 255) / 256, 256, 0, S.stream>>>(m, x, cval, Jout, S.ldj);
+    const int npl = (int)(S.n_loc / 3), i0 = (int)(S.col0 / 3);
+    if (S.world > 1) cudaMemsetAsync(cval, 0, (size_t)m * sizeof(double), S.stream);    // the other ranks' rows: summed in below
+    thomson_c_kernel<<<(npl + 255) / 256, 256, 0, S.stream>>>(npl, i0, x, cval, Jout, S.ldj);
+    if (S.world > 1) comm_allreduce(S, cval, m);
     S.launches += 2;
   }
 }
 // per outer iteration: whatever of the Lagrangian Hessian depends only on (x, lambda)
 static void fam_hess_prepare(LargeState &S, const double *x, const double *lam) {
-  if (S.family == LFPSQP_FAM_HOST) {  // the closure of optimize.jl:227-231 reads the current x and lambda: cache them on the host
+  if (S.family == LFPSQP_FAM_THOMSON) {  // all-gathered coordinates of the point the Hessian is taken at (once per outer iteration)
+    if (S.world > 1) thomson_gather(S, x, S.xfull_h);
+  } else if (S.family == LFPSQP_FAM_HOST) {  // the closure of optimize.jl:227-231 reads the current x and lambda: cache them on the host
     host_x(S, x);
     if (S.m > 0) { cudaMemcpyAsync(S.hlam, lam, S.m * sizeof(double), cudaMemcpyDeviceToHost, S.stream); cudaStreamSynchronize(S.stream); }
   } else if (S.family == LFPSQP_FAM_DIAGQUAD) {  // hdiag = w + Q' lambda : one pass over Q
@@ -254,12 +270,14 @@ static int fam_hess(LargeState &S, double *dest, const double *src, const double
     S.launches++;
     return S.vgrid;
   } else {
-    int np = (int)(S.n / 3);
-    dim3 grid; thomson_grid(S, np, grid);
-    thomson_pair_kernel<2><<<grid, 256, 0, S.stream>>>(np, x, src, S.pairws, nullptr, 0, S.ctrl, pred);
-    thomson_reduce_kernel<2><<<(3 * np + 255) / 256, 256, 0, S.stream>>>(np, grid.y, S.pairws, src, lam, dest, S.lp, 0, S.ctrl, pred);
+    const int np = (int)(S.n / 3), npl = (int)(S.n_loc / 3), i0 = (int)(S.col0 / 3);
+    const double *xf = (S.world > 1) ? S.xfull_h : x;            // gathered by fam_hess_prepare
+    const double *vf = thomson_gather(S, src, S.vfull);
+    dim3 grid; thomson_grid(S, npl, grid);
+    thomson_pair_kernel<2><<<grid, 256, 0, S.stream>>>(np, i0, npl, xf, vf, S.pairws, nullptr, 0, S.ctrl, pred);
+    thomson_reduce_kernel<2><<<(3 * npl + 255) / 256, 256, 0, S.stream>>>(npl, grid.y, S.pairws, src, lam + i0, dest, S.lp, 0, S.ctrl, pred);
     S.launches += 2;
-    return (3 * np + 255) / 256;
+    return (3 * npl + 255) / 256;
   }
 }
 
@@ -1017,8 +1035,8 @@ extern "C" int lfpsqp_large_setup(lfpsqp_ctx *c, int family, int64_t n_global, i
   if (n_global < 1 || m < 0 || n_loc < 1 || col0 < 0 || col0 + n_loc > n_global || m > n_global)
     return c->fail(LFPSQP_ERR_ARG, "bad sizes for large-n setup");
   if (c->comm.world <= 1 && n_loc != n_global) return c->fail(LFPSQP_ERR_ARG, "a column shard needs a communicator (lfpsqp_comm_init)");
-  if (family == LFPSQP_FAM_THOMSON && (n_global % 3 || m != n_global / 3 || n_loc != n_global))
-    return c->fail(LFPSQP_ERR_FAMILY, "THOMSON needs n = 3 m and runs on one GPU (its callbacks need all of x)");
+  if (family == LFPSQP_FAM_THOMSON && (n_global % 3 || m != n_global / 3 || n_loc % 3 || col0 % 3))
+    return c->fail(LFPSQP_ERR_FAMILY, "THOMSON needs n = 3 m and column shards of whole points (col0 and n_loc multiples of 3)");
   if (m > 16384) return c->fail(LFPSQP_ERR_ARG, "m too large for the replicated factor");
   if (family == LFPSQP_FAM_HOST) {
     const lfpsqp_host_callbacks *cb = (const lfpsqp_host_callbacks *)params;
@@ -1030,7 +1048,6 @@ extern "C" int lfpsqp_large_setup(lfpsqp_ctx *c, int family, int64_t n_global, i
   LargeState *Sp = new LargeState(); LargeState &S = *Sp;
   c->large = Sp;
   S.comm = &c->comm; S.world = c->comm.world > 1 ? c->comm.world : 1; S.rank = c->comm.rank;
-  if (S.world > 1 && family == LFPSQP_FAM_THOMSON) return c->fail(LFPSQP_ERR_FAMILY, "THOMSON is single-GPU");
   S.family = family; S.n = n_global; S.n_loc = n_loc; S.nv = n_loc; S.col0 = col0; S.m = (int)m; S.stream = c->stream;
   S.sm_count = c->sm_count; S.ldj = up2(n_loc); S.ldm = up2(std::max<int64_t>(m, 1));
   S.vgrid = (int)std::min<int64_t>(std::max<int64_t>((n_loc + 255) / 256, 1), std::min<int64_t>(MAXP, 4 * (int64_t)c->sm_count));
@@ -1059,7 +1076,10 @@ extern "C" int lfpsqp_large_setup(lfpsqp_ctx *c, int family, int64_t n_global, i
   ok &= dalloc(S, &S.cpart, (size_t)S.nsplit * std::max(nl, mm) + 2);
   ok &= dalloc(S, &S.lp, (size_t)NSLOT * MAXP); ok &= dalloc(S, &S.gpart, (size_t)NSLOT * MAXP);
   ok &= dalloc(S, &S.ctrl, 1); ok &= dalloc(S, &S.commbuf, 64);
-  if (family == LFPSQP_FAM_THOMSON) ok &= dalloc(S, &S.pairws, (size_t)16 * nl + 2);
+  if (family == LFPSQP_FAM_THOMSON) {
+    ok &= dalloc(S, &S.pairws, (size_t)16 * nl + 2);
+    if (S.world > 1) { ok &= dalloc(S, &S.xfull, (size_t)n_global + 2); ok &= dalloc(S, &S.xfull_h, (size_t)n_global + 2); ok &= dalloc(S, &S.vfull, (size_t)n_global + 2); }
+  }
   S.Dnr = nullptr;
   if (family == LFPSQP_FAM_HOST) {
     S.cb = *(const lfpsqp_host_callbacks *)params;

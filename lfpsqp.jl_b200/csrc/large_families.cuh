@@ -64,22 +64,25 @@ __global__ void __launch_bounds__(256) dq_rows_kernel(const double *__restrict__
   }
 }
 
-// ================================================================== THOMSON (BASELINE config C4), single-GPU shard
-// Pairwise O(N^2) kernels on a 2-D grid: blockIdx.x = block of 256 points i, blockIdx.y = chunk of the j range (so
+// ================================================================== THOMSON (BASELINE config C4)
+// Pairwise O(N^2) kernels on a 2-D grid: blockIdx.x = block of 256 OWNED points i, blockIdx.y = chunk of the j range (so
 // that N = 4096 fills the GPU: 16 x 16 CTAs instead of 16).  Points j are staged through shared memory.
+// Column-sharded: this rank owns the points [i0, i0 + npl) (their 3 npl coordinates are its columns of J
+// and its entries of every n-vector); x / v are the ALL-GATHERED coordinates of all np_ points, outputs are local.
 // mode 0: f partials (sum_{j!=i} 1/r_ij, halved)                       -> part slot s0 [blockIdx.y * gridDim.x + blockIdx.x]
 // mode 1: partial gradient   -sum_j (x_i-x_j)/r^3                      -> ws[blockIdx.y][3 i ..]
 // mode 2: partial Hessian action sum_j [3 r (r.w)/r^5 - w/r^3], w = v_i - v_j  -> ws[blockIdx.y][3 i ..]
 template <int MODE>
-__global__ void __launch_bounds__(256) thomson_pair_kernel(int np_, const double *__restrict__ x, const double *__restrict__ v,
+__global__ void __launch_bounds__(256) thomson_pair_kernel(int np_, int i0, int npl, const double *__restrict__ x, const double *__restrict__ v,
                                                            double *__restrict__ ws, double *part, int s0,
                                                            const LargeCtrl *ctrl, int pred) {
   if (pred == 1 && ctrl->status != 0) return;
   __shared__ double xs[256 * 3];
   __shared__ double vs[MODE == 2 ? 256 * 3 : 3];
   __shared__ double sh[33];
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  const bool act = i < np_;
+  const int il = blockIdx.x * 256 + threadIdx.x;      // local index of the owned point
+  const int i = i0 + il;
+  const bool act = il < npl;
   const int jlen = (np_ + gridDim.y - 1) / gridDim.y, jbeg = blockIdx.y * jlen, jend = min(np_, jbeg + jlen);
   double xi = 0, yi = 0, zi = 0, vx = 0, vy = 0, vz = 0;
   if (act) { xi = x[3 * i]; yi = x[3 * i + 1]; zi = x[3 * i + 2]; if (MODE == 2) { vx = v[3 * i]; vy = v[3 * i + 1]; vz = v[3 * i + 2]; } }
@@ -108,7 +111,7 @@ __global__ void __launch_bounds__(256) thomson_pair_kernel(int np_, const double
     double pr = block_sum(act ? 0.5 * a0 : 0.0, sh);
     if (threadIdx.x == 0) part[(size_t)s0 * MAXP + blockIdx.y * gridDim.x + blockIdx.x] = pr;
   } else if (act) {
-    double *o = ws + (size_t)blockIdx.y * 3 * np_ + 3 * i;
+    double *o = ws + (size_t)blockIdx.y * 3 * npl + 3 * il;
     o[0] = a0; o[1] = a1; o[2] = a2;
   }
 }
@@ -133,13 +136,15 @@ __global__ void __launch_bounds__(256) thomson_reduce_kernel(int np_, int chunks
     if (threadIdx.x == 0) part[(size_t)s0 * MAXP + blockIdx.x] = pr;
   }
 }
-// c_i = |x_i|^2 - 1 ; optionally the three structural non-zeros of row i of the (dense-treated) Jacobian
-__global__ void thomson_c_kernel(int np_, const double *__restrict__ x, double *__restrict__ cval, double *J, int64_t ld) {
+// c_i = |x_i|^2 - 1 for the owned points (x = this rank's coordinates; cval rows of the other ranks are left untouched:
+// zeroed by the caller and summed over the ranks) ; optionally the three structural non-zeros of row i0 + i of the
+// (dense-treated) Jacobian shard
+__global__ void thomson_c_kernel(int npl, int i0, const double *__restrict__ x, double *__restrict__ cval, double *J, int64_t ld) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= np_) return;
+  if (i >= npl) return;
   double a = x[3 * i], b = x[3 * i + 1], c = x[3 * i + 2];
-  cval[i] = a * a + b * b + c * c - 1.0;
-  if (J) { double *r = J + (int64_t)i * ld + 3 * i; r[0] = 2.0 * a; r[1] = 2.0 * b; r[2] = 2.0 * c; }
+  cval[i0 + i] = a * a + b * b + c * c - 1.0;
+  if (J) { double *r = J + (int64_t)(i0 + i) * ld + 3 * i; r[0] = 2.0 * a; r[1] = 2.0 * b; r[2] = 2.0 * c; }
 }
 
 }  // namespace lfpsqp

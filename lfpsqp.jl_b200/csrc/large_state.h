@@ -54,6 +54,7 @@ struct LargeState {
   // m vectors (replicated on every rank)
   double *cval = nullptr, *lam = nullptr, *tm = nullptr, *ty = nullptr, *tu = nullptr, *nr_t1 = nullptr, *nr_t2 = nullptr,
          *nr_dc = nullptr;
+  double *xfull = nullptr, *xfull_h = nullptr, *vfull = nullptr;   // THOMSON column-sharded: all-gathered coordinates (scratch / Hessian point / direction)
   double *cpart = nullptr;   // pass-2 partial column sums [nsplit][n_loc]
   int nsplit = 1, rows_per_split = 1;
   double *lp = nullptr, *gpart = nullptr, *commbuf = nullptr;   // loop partials, generic partials [NSLOT][MAXP]

@@ -32,6 +32,17 @@ def column_range(n, world, rank):
     return 2 * lo, 2 * (hi - lo)
 
 
+def thomson_point_range(npoints, world, rank):
+    """Thomson shards whole points with an even count per rank: returns (col0, n_loc) = 3 x the owned point range."""
+    pairs = npoints // 2
+    if npoints % 2:
+        raise _lib.LFPSQPError("column-sharded Thomson needs an even number of points")
+    base, rem = divmod(pairs, world)
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return 6 * lo, 6 * (hi - lo)
+
+
 def find_nccl():
     """Path of the NCCL library torch itself uses (nvidia-nccl wheel), or None to let the loader search."""
     try:

@@ -41,6 +41,47 @@ for (n, m, nr) in [(4096, 200, False), (1000, 130, False), (4096, 200, True)]:
             abs(obj[-1] - oobj[-1]) / abs(oobj[-1]), rel(lam, olam), status, "OK" if ok else "MISMATCH"), flush=True)
     dist.barrier()
 
+# ---- Thomson column-sharded: whole points per rank, x / v all-gathered per callback evaluation
+for npts in (64, 128):
+    rng = np.random.default_rng(6)
+    x0 = rng.standard_normal((npts, 3)); x0 /= np.linalg.norm(x0, axis=1, keepdims=True); x0 = x0.ravel()
+    col0, nloc = D.thomson_point_range(npts, world, rank)
+    P = L.LargeProblem(L.families.thomson(npts), ctx, col0=col0, n_loc=nloc, n_global=3 * npts)
+    x, obj, lam, info, st, status = P.solve(x0[col0:col0 + nloc], L.LFPSQPParams(), return_stats=True)
+    parts = [None] * world
+    dist.all_gather_object(parts, (col0, x))
+    if rank == 0:
+        from oracle import oracle as O
+        xfull = np.concatenate([p[1] for p in sorted(parts, key=lambda p: p[0])])
+        ox, oobj, olam, ot, ost = O.optimize("thomson", 3 * npts, npts, 0, x0)
+        with O.variant("fma"):
+            fx = O.optimize("thomson", 3 * npts, npts, 0, x0)[0]
+        ok = (int(info.condition) == ot["condition"] and abs(info.iter - ot["iter"]) <= 1 and
+              (rel(xfull, ox) <= 1e-8 or rel(xfull, ox) <= 10 * rel(fx, ox)) and abs(obj[-1] - oobj[-1]) <= 1e-9 * abs(oobj[-1]))
+        print("world=%d THOMSON N=%d: gpu %s %d orc %d %d  x err %.2e (oracle-fma %.2e) f err %.2e lam err %.2e status %d -> %s" % (
+            world, npts, info.condition.name, info.iter, ot["condition"], ot["iter"], rel(xfull, ox), rel(fx, ox),
+            abs(obj[-1] - oobj[-1]) / abs(oobj[-1]), rel(lam, olam), status, "OK" if ok else "MISMATCH"), flush=True)
+    dist.barrier()
+
+if "c4" in sys.argv:   # BASELINE config C4 (Thomson N = 4096) column-sharded: first 10 outer iterations, wall + phases
+    import time, warnings
+    npts = 4096
+    rng = np.random.Generator(np.random.Philox(key=4))
+    p0 = rng.standard_normal((npts, 3)); p0 /= np.linalg.norm(p0, axis=1, keepdims=True); p0 = p0.ravel()
+    col0, nloc = D.thomson_point_range(npts, world, rank)
+    P = L.LargeProblem(L.families.thomson(npts), ctx, col0=col0, n_loc=nloc, n_global=3 * npts)
+    for rep in range(2):
+        dist.barrier()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            t0 = time.perf_counter()
+            x, obj, lam, info, st, status = P.solve(p0[col0:col0 + nloc], L.LFPSQPParams(maxiter=10), return_stats=True)
+            wall = time.perf_counter() - t0
+        ph = P.phase_ms()
+        if rank == 0:
+            print("C4 world=%d: 10 outer iterations %.1f ms wall | factor %.1f projcg %.1f linesearch %.1f | projcg iters %d | f %.6f -> %.6f" % (
+                world, wall * 1e3, ph["factor"], ph["projcg"], ph["linesearch"], st["projcg_iters"], obj[0], obj[-1]), flush=True)
+
 # ---- finite bounds (2n embedding) column-sharded: every rank passes its slice of xl, xu
 for (n, m, seed, nr) in [(256, 16, 2, False), (256, 16, 2, True), (512, 32, 1, True)]:
     Q, A, b, xt, w, x0 = L.make_diagquad(n, m, seed=seed, cond=50.0)
