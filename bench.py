@@ -214,7 +214,7 @@ def large_n_section(L, ctx, torch, dev, with_cpu, dist=None, rank=0, world=1, we
                                                                      else "pcg_a + rows_dot + cols_dot + pcg_z + pcg_x"),
                                           "achieved": pcg_bytes / (pcg_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                                           "frac": pcg_bytes / (pcg_ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes_per_iteration_per_gpu": pcg_bytes,
-                                          "traffic": None}}
+                                          "traffic": (_traffic("fused_pcg_kernel", "bytes_per_iteration") if (world == 1 and not weak) else None)}}
     try:
         dmma = ctx.fp64_peak("dmma")
         flops = float(m) * (m + 1) * nloc
@@ -305,6 +305,17 @@ def extras_section(L, ctx, torch, dev, with_cpu):
                                     "mean_outer_iterations": float(lens.mean() - 1),
                                     "golden_instance0": {"iter": int(term0["iter"]), "condition": int(term0["condition"]), "f_diff": float(term0["f_diff"])},
                                     "hbm_io_gbs": io / (kms * 1e-3) / 1e9}
+    try:   # binding roof of the thread-per-instance kernel: FP64 issue (HBM sees 0.05 of its peak)
+        from oracle import oracle as O
+        fl = float(O.optimize_batched("rosenbrock", 2, 0, 0, x0[:1 << 14], H=H, nthreads=host_cores())[5]["flops"].mean())
+        dfma = ctx.fp64_peak("dfma")
+        out["c3_rosenbrock_batched"]["roofline"] = {"bound": "fp64-issue", "flops_per_instance": fl, "achieved": fl * B / (kms * 1e-3) / 1e12,
+                                                    "peak": dfma, "unit": "TFLOP/s", "frac": fl * B / (kms * 1e-3) / 1e12 / dfma,
+                                                    "peak_source": "DFMA microbenchmark measured in this run",
+                                                    "note": "algorithmic flops = the oracle's instrumented FP64 op count; n = 2, so the work per "
+                                                            "instance is divisions, square roots and branches of the driver, not vector arithmetic"}
+    except Exception as e:  # noqa
+        out["c3_rosenbrock_batched"]["roofline"] = {"error": repr(e)}
     if with_cpu:
         from oracle import oracle as O
         S = 1 << 17
@@ -402,6 +413,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")   # host-side waits (an NCCL barrier would keep a kernel spinning on the idle GPUs)
     dev = torch.device("cuda", local_rank)
     ctx = L.Context(local_rank)
     stream = torch.cuda.current_stream()
@@ -501,6 +513,7 @@ def main():
         # devices and lfpsqp_solve_batched shards the N*B instances inside the library (one host thread + stream pipeline
         # per device, no collective); the other ranks only wait.
         barrier()
+        dist.barrier(group=cpu_group)
         one_call = 0.0
         if rank == 0:
             mc = L.MultiContext(list(range(world)))
@@ -526,6 +539,7 @@ def main():
             one_call = BW * K / (time.perf_counter() - t0)
             assert np.array_equal(g_x[:B], h_x), "multi-GPU one-call result differs from the per-process result"
             mc.close()
+        dist.barrier(group=cpu_group)     # the other ranks wait on the host: their GPUs are driven by rank 0's context meanwhile
         barrier()
         e2e_modes["one_call_multi_ctx"] = max_over_ranks(one_call)
         e2e_value = max(e2e_modes.values())

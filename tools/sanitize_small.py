@@ -47,3 +47,28 @@ if mode in ("all", "new"):
     print(L.optimize(f, grad, c, jac, hlv, x0, x0 - 0.5, x0 + 0.7, 4, L.LFPSQPParams(maxiter=3))[3])
     Q, A, b, xt, w, x0 = L.make_diagquad(65, 3, seed=6, cond=50.0)   # odd n through the callbacks
     print(L.optimize(f, grad, c, jac, hlv, x0, None, None, 3, L.LFPSQPParams(maxiter=2))[3])
+if mode in ("all", "r2"):
+    # round-2 additions: lane-group register kernel (LW = 8 / 16, group-masked shuffles, shared-memory stash), caller-supplied
+    # noise rows, multi-device context, rank-deficient large-n path (Jacobi eigen-solver), explicit-inverse guard fallback
+    co = rng.standard_normal((37, 50)); inf = np.inf * np.ones(50)                # 37: groups of a warp with and without work
+    fam = L.families.readme_inequality(co)
+    print(L.optimize_batched(fam.f, None, fam.d, np.zeros((37, 50)), -inf, inf, 0, 1)[4]["iter"][:6])
+    nz = rng.standard_normal((37, 3, 102))
+    print(L.optimize_batched(fam.f, None, fam.d, np.zeros((37, 50)), -inf, inf, 0, 1, L.LFPSQPParams(beta=1e-2, t_beta=3), noise=nz)[4]["iter"][:6])
+    co = rng.standard_normal((9, 20)); inf = np.inf * np.ones(20)                 # LW = 16, NPL = 2 instantiation
+    fam = L.families.readme_inequality(co)
+    print(L.optimize_batched(fam.f, None, fam.d, np.zeros((9, 20)), -inf, inf, 0, 1)[4]["iter"])
+    t = 2 * rng.standard_normal((5, 12)); xl = np.r_[-np.inf * np.ones(6), -0.5 * np.ones(6)]; xu = np.r_[np.inf * np.ones(3), 0.4 * np.ones(9)]
+    fam = L.families.boxquad(t, a=np.ones(12), b=3.0)
+    print(L.optimize_batched(fam.f, fam.c, np.tile(np.clip(np.zeros(12), xl, xu) + 0.25, (5, 1)), xl, xu, 1)[4]["iter"])
+    mc = L.MultiContext([0])
+    print(L.optimize_batched(L.families.rosenbrock().f, rng.uniform(-2, 2, (33, 2)), ctx=mc)[4]["iter"][:4]); mc.close()
+    Q, A, b, xt, w, x0 = L.make_diagquad(96, 12, seed=9, cond=50.0)
+    Q[11] = Q[0]; A[11] = A[0]; b[11] = b[0]                                     # duplicated constraint -> pseudo-inverse path
+    P = L.LargeProblem(L.families.diagquad(Q, A, b, xt, w))
+    print(P.factor(x0, want=())["rank_deficient"], P.solve(x0, L.LFPSQPParams(maxiter=3))[3])
+    os.environ["LFPSQP_EXPLICIT_INVERSE"] = "0"                                  # two triangular phases in the fused projcg
+    Q, A, b, xt, w, x0 = L.make_diagquad(96, 12, seed=10, cond=50.0)
+    P = L.LargeProblem(L.families.diagquad(Q, A, b, xt, w)); P.factor(x0, want=())
+    print(P.projcg(x0, lam=np.zeros(12), tol=1e-8, maxit=20)["iters"])
+    del os.environ["LFPSQP_EXPLICIT_INVERSE"]
