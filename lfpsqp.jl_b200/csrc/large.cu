@@ -52,6 +52,11 @@ static int read_ctrl(lfpsqp_ctx *c, LargeState &S) {
   CK(cudaStreamSynchronize(S.stream));
   CK(cudaGetLastError());   // a refused launch (bad configuration) since the last check must not pass silently
   if (S.hctrl->commfail) return c->fail(LFPSQP_ERR_COMM, "a peer-memory exchange of the column-sharded mode timed out (a rank died or fell > 4 s behind)");
+  if (S.nz_pending) {       // density of the zero-slab map of J -> keep skipping (block-sparse J) or use the plain SYRK from now on
+    S.nz_pending = false;
+    const double total = (double)S.nz_rows * (double)std::max<int64_t>(S.nz_ld, 1);
+    S.gram_mode = ((double)S.hctrl->nz_count > 0.5 * total) ? 2 : 1;
+  }
   if (S.guard_pending) {    // pivots of the factor just computed -> which solve the fused projcg kernel may use
     S.guard_pending = false;
     const double lo = S.hctrl->ldiag_min, hi = S.hctrl->ldiag_max;   // ~lambda_min(G) (from above), trace(G)
@@ -68,7 +73,7 @@ static void write_ctrl_fields(LargeState &S) {  // push the host copy (tolerance
 
 // C (op)= A B' with optional split-K through S.gemm_ws
 static void gemm_nt(LargeState &S, int M, int N, int K, const double *A, int64_t lda, const double *B, int64_t ldb, double *C,
-                    int64_t ldc, int mode, int lower) {
+                    int64_t ldc, int mode, int lower, const GemmExt *ext = nullptr) {
   if (M <= 0 || N <= 0) return;
   const bool narrow = (N <= 64);
   const int BN = narrow ? 64 : 128;
@@ -76,7 +81,15 @@ static void gemm_nt(LargeState &S, int M, int N, int K, const double *A, int64_t
   int tiles = grid.x * grid.y;
   if (lower) tiles = (tiles + grid.y) / 2;
   int ksplit = 1;
-  if (mode != GEMM_SUB && tiles * 2 <= S.sm_count && K >= 1024) {
+  GemmExt X; if (ext) X = *ext;
+  if (X.batch > 1) {   // independent products of one shape: blockIdx.z = product
+    grid.z = X.batch;
+    if (narrow) dgemm_nt_kernel<64><<<grid, 256, dgemm_smem_bytes<64>(), S.stream>>>(M, N, K, A, lda, B, ldb, C, ldc, mode, lower, 1, 0, X);
+    else dgemm_nt_kernel<128><<<grid, 256, dgemm_smem_bytes<128>(), S.stream>>>(M, N, K, A, lda, B, ldb, C, ldc, mode, lower, 1, 0, X);
+    S.launches++;
+    return;
+  }
+  if (mode != GEMM_SUB && tiles * 2 <= S.sm_count && K >= 1024 && !X.tri) {
     ksplit = std::min(std::min(16, S.sm_count / tiles), K / 256);
     while (ksplit > 1 && (size_t)ksplit * M * N * 8 > S.gemm_ws_bytes) ksplit--;
     if (ksplit < 1) ksplit = 1;
@@ -92,15 +105,21 @@ static void gemm_nt(LargeState &S, int M, int N, int K, const double *A, int64_t
     }
     ksplit = best;
   }
+  // zero-slab skipping (SYRK of a block-sparse J): the chunk list of one K slice must fit behind the tiles in shared memory
+  const int kchunks = (K + GM_BK - 1) / GM_BK, per = (kchunks + ksplit - 1) / ksplit;
+  const size_t skip_smem = dgemm_smem_bytes<128>() + (size_t)per * sizeof(int);
+  const bool skip = X.nz && !narrow && skip_smem <= (size_t)S.max_dyn_smem;
   if (ksplit == 1) {
-    if (narrow) dgemm_nt_kernel<64><<<grid, 256, dgemm_smem_bytes<64>(), S.stream>>>(M, N, K, A, lda, B, ldb, C, ldc, mode, lower, 1, 0);
-    else dgemm_nt_kernel<128><<<grid, 256, dgemm_smem_bytes<128>(), S.stream>>>(M, N, K, A, lda, B, ldb, C, ldc, mode, lower, 1, 0);
+    if (skip) dgemm_nt_kernel<128, true><<<grid, 256, skip_smem, S.stream>>>(M, N, K, A, lda, B, ldb, C, ldc, mode, lower, 1, 0, X);
+    else if (narrow) dgemm_nt_kernel<64><<<grid, 256, dgemm_smem_bytes<64>(), S.stream>>>(M, N, K, A, lda, B, ldb, C, ldc, mode, lower, 1, 0, X);
+    else dgemm_nt_kernel<128><<<grid, 256, dgemm_smem_bytes<128>(), S.stream>>>(M, N, K, A, lda, B, ldb, C, ldc, mode, lower, 1, 0, X);
     S.launches++;
   } else {
     grid.z = ksplit;
     const int64_t stride = (int64_t)M * N;
-    if (narrow) dgemm_nt_kernel<64><<<grid, 256, dgemm_smem_bytes<64>(), S.stream>>>(M, N, K, A, lda, B, ldb, S.gemm_ws, N, GEMM_ASSIGN, lower, ksplit, stride);
-    else dgemm_nt_kernel<128><<<grid, 256, dgemm_smem_bytes<128>(), S.stream>>>(M, N, K, A, lda, B, ldb, S.gemm_ws, N, GEMM_ASSIGN, lower, ksplit, stride);
+    if (skip) dgemm_nt_kernel<128, true><<<grid, 256, skip_smem, S.stream>>>(M, N, K, A, lda, B, ldb, S.gemm_ws, N, GEMM_ASSIGN, lower, ksplit, stride, X);
+    else if (narrow) dgemm_nt_kernel<64><<<grid, 256, dgemm_smem_bytes<64>(), S.stream>>>(M, N, K, A, lda, B, ldb, S.gemm_ws, N, GEMM_ASSIGN, lower, ksplit, stride, X);
+    else dgemm_nt_kernel<128><<<grid, 256, dgemm_smem_bytes<128>(), S.stream>>>(M, N, K, A, lda, B, ldb, S.gemm_ws, N, GEMM_ASSIGN, lower, ksplit, stride, X);
     const double *ws = S.gemm_ws;
     const double sgn = (mode == GEMM_ASSIGN_NEG) ? -1.0 : 1.0;
     const int lo = lower;
@@ -314,10 +333,25 @@ static void y_retract(LargeState &S, double *vn, const double *vb) {  // y_retra
 }
 
 template <class T> static bool dalloc(LargeState &S, T **p, size_t count);
+// G (lower tiles) = Jg Jg'.  Jg is stored dense; unless it was found dense before, a one-pass scan marks the all-zero
+// (64 rows x 16 columns) slabs and the SYRK skips K chunks that contribute nothing (Thomson: 24 of 768 chunks per diagonal tile).
+static void gram_syrk(LargeState &S, const double *Jg) {
+  const int m = S.m;
+  GemmExt X; const GemmExt *ext = nullptr;
+  if (S.gram_mode != 2 && S.nzmap && m > 64) {
+    cudaMemsetAsync(&S.ctrl->nz_count, 0, sizeof(unsigned long long), S.stream);
+    dim3 sg((unsigned)((S.n_loc + 1023) / 1024), (unsigned)S.nz_rows);
+    zero_slab_map_kernel<<<sg, 256, 0, S.stream>>>(Jg, S.ldj, m, S.n_loc, S.nzmap, S.nz_ld, &S.ctrl->nz_count);
+    S.launches++;
+    X.nz = S.nzmap; X.nz_ld = S.nz_ld; X.nz_rows = S.nz_rows; ext = &X;
+    if (S.gram_mode == 0) S.nz_pending = true;
+  }
+  gemm_nt(S, m, m, (int)S.n_loc, Jg, S.ldj, Jg, S.ldj, S.G, S.ldm, GEMM_ASSIGN, 1, ext);
+}
 static void gram_only(LargeState &S) {   // S.G (lower tiles) = J W J', all-reduced
   const int m = S.m;
   const double *Jg = S.ineq ? S.Jw : S.J;    // Jw = J diag(Dy) was formed by the factorize() call that precedes
-  gemm_nt(S, m, m, (int)S.n_loc, Jg, S.ldj, Jg, S.ldj, S.G, S.ldm, GEMM_ASSIGN, 1);
+  gram_syrk(S, Jg);
   if (S.world > 1) comm_allreduce(S, S.G, (size_t)m * S.ldm);
 }
 // Truncated path of optimize.jl:297-302 in Gram form: G = V diag(lambda) V' (Jacobi, large_eig.cu), G^+ into S.Ginv.
@@ -354,7 +388,7 @@ static int factorize(lfpsqp_ctx *c, LargeState &S) {
     Jg = S.Jw;
   }
   cudaEventRecord(S.ev_g0, S.stream);
-  gemm_nt(S, m, m, (int)S.n_loc, Jg, S.ldj, Jg, S.ldj, S.G, ldm, GEMM_ASSIGN, 1);   // SYRK, lower tiles
+  gram_syrk(S, Jg);   // SYRK, lower tiles
   cudaEventRecord(S.ev_g1, S.stream);
   if (S.world > 1) comm_allreduce(S, S.G, (size_t)m * ldm);
   if (S.prefer_pinv) return factorize_pinv(c, S, false);   // this problem lost rank before: go straight to the eigen-decomposition
@@ -391,20 +425,32 @@ static int factorize(lfpsqp_ctx *c, LargeState &S) {
       gemm_nt(S, rem2, rem2, nb, A21 + (int64_t)nb2 * ldm, ldm, A21 + (int64_t)nb2 * ldm, ldm, A22 + (int64_t)nb2 * ldm + nb2, ldm, GEMM_SUB, 1);
     if (side_s != main_s) cudaStreamWaitEvent(main_s, S.ev_potf, 0);
   }
-  // XT = L^-T (upper triangular, row-major), block row by block row; Linv = XT'
+  // XT = L^-T (upper triangular, row-major) and Linv = L^-1 by recursive doubling from the inverted diagonal blocks:
+  //   [L11 0; L21 L22]^-1 = [L11^-1 0; -L22^-1 L21 L11^-1, L22^-1]   i.e.  XT12 = -(XT11 L21') Linv22'
+  // Per level (block size B = NB, 2 NB, ...): two batched DMMA GEMMs over all pairs of adjacent blocks (the triangular operand
+  // bounds the K loop of each tile) + one batched transpose XT12 -> Linv21: 3 launches per level instead of 3 per block row.
   cudaMemsetAsync(S.XT, 0, (size_t)m * ldm * sizeof(double), S.stream);
-  for (int b = 0; b < nblk; b++) {
-    int i0 = b * NB, nb = std::min(NB, m - i0);
-    double *Db = S.Dblk + (size_t)b * NB * NB;
-    copy_block_T_kernel<<<(NB * NB + 255) / 256, 256, 0, S.stream>>>(Db, NB, nb, S.XT + (int64_t)i0 * ldm + i0, ldm);
-    S.launches++;
-    if (i0 > 0) {
-      gemm_nt(S, i0, nb, i0, S.XT, ldm, S.G + (int64_t)i0 * ldm, ldm, S.tmp64, NB, GEMM_ASSIGN, 0);   // P' = XT * L_i'
-      gemm_nt(S, i0, nb, nb, S.tmp64, NB, Db, NB, S.XT + i0, ldm, GEMM_ASSIGN_NEG, 0);              // XT[:, blk] = -P' D_i'
+  cudaMemsetAsync(S.Linv, 0, (size_t)m * ldm * sizeof(double), S.stream);
+  diag_blocks_kernel<<<nblk, 256, 0, S.stream>>>(S.Dblk, NB, m, S.XT, S.Linv, ldm);
+  S.launches++;
+  for (int B = NB; B < m; B *= 2) {
+    const int nfull = m / (2 * B);                      // pairs with two complete blocks
+    const int o_r = nfull * 2 * B, B2r = m - o_r - B;   // ragged last pair: L22 is B2r x B2r (if > 0)
+    for (int part = 0; part < 2; part++) {
+      const int np = part == 0 ? nfull : (B2r > 0 ? 1 : 0);
+      if (np <= 0) continue;
+      const int o = part == 0 ? 0 : o_r, B2 = part == 0 ? B : B2r;
+      const int64_t pstride = (int64_t)2 * B * ldm + 2 * B;
+      double *Tt = S.gemm_ws;                             // B x B2 per pair, ld B
+      GemmExt e1; e1.batch = np; e1.batch_a = pstride; e1.batch_b = pstride; e1.batch_c = (int64_t)B * B; e1.tri = 1;
+      gemm_nt(S, B, B2, B, S.XT + (int64_t)o * ldm + o, ldm, S.G + (int64_t)(o + B) * ldm + o, ldm, Tt, B, GEMM_ASSIGN, 0, &e1);
+      GemmExt e2; e2.batch = np; e2.batch_a = (int64_t)B * B; e2.batch_b = pstride; e2.batch_c = pstride; e2.tri = 2;
+      gemm_nt(S, B, B2, B2, Tt, B, S.Linv + (int64_t)(o + B) * ldm + (o + B), ldm, S.XT + (int64_t)o * ldm + (o + B), ldm, GEMM_ASSIGN_NEG, 0, &e2);
+      dim3 tg((B2 + 31) / 32, (B + 31) / 32, np);
+      transpose_kernel<<<tg, 256, 0, S.stream>>>(S.XT + (int64_t)o * ldm + (o + B), ldm, S.Linv + (int64_t)(o + B) * ldm + o, ldm, B, B2, pstride, pstride);
+      S.launches++;
     }
   }
-  dim3 tg((m + 31) / 32, (m + 31) / 32);
-  transpose_kernel<<<tg, 256, 0, S.stream>>>(S.XT, ldm, S.Linv, ldm, m, m);
   if (S.fused_ok && S.Ginv) {   // G^-1 = L^-T L^-1 = XT XT' for the fused projcg kernel (large_fused.cu): one more DMMA GEMM, m^3 flops
     gemm_nt(S, m, m, m, S.XT, ldm, S.XT, ldm, S.Ginv, ldm, GEMM_ASSIGN, 0);
     // guard of that shortcut: kappa = trace(G) * lambda_max(G^-1) >= cond(G) (8 power iterations on G^-1, ~0.1 ms); read_ctrl
@@ -1067,6 +1113,9 @@ extern "C" int lfpsqp_large_setup(lfpsqp_ctx *c, int family, int64_t n_global, i
   ok &= dalloc(S, &S.J, mm * S.ldj);
   ok &= dalloc(S, &S.G, mm * S.ldm); ok &= dalloc(S, &S.XT, mm * S.ldm); ok &= dalloc(S, &S.Linv, mm * S.ldm);
   ok &= dalloc(S, &S.Dblk, ((mm + 63) / 64) * 64 * 64); ok &= dalloc(S, &S.tmp64, mm * 64); ok &= dalloc(S, &S.thresh, 8);
+  S.nz_rows = (int)((mm + 63) / 64); S.nz_ld = (int64_t)((S.ldj + GM_BK - 1) / GM_BK + 64) / 64 * 64; S.gram_mode = 0; S.nz_pending = false;
+  ok &= dalloc(S, &S.nzmap, (size_t)S.nz_rows * S.nz_ld);
+  { int dev = 0, v = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev); if (v > 2048) S.max_dyn_smem = v - 1024; }
   S.gemm_ws_bytes = std::max<size_t>((size_t)16 * mm * 64 * 8, std::min<size_t>(mm * mm * 8 * 16, (size_t)1 << 30));
   { char *ws = nullptr; ok &= dalloc(S, &ws, S.gemm_ws_bytes); S.gemm_ws = (double *)ws; }
   double **vecs[] = {&S.x, &S.xnew, &S.xtil, &S.g, &S.d, &S.nd, &S.w0, &S.w1, &S.w2, &S.w3, &S.w4, &S.hdiag};
@@ -1112,6 +1161,8 @@ extern "C" int lfpsqp_large_setup(lfpsqp_ctx *c, int family, int64_t n_global, i
   }
   cudaFuncSetAttribute(dgemm_nt_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgemm_smem_bytes<128>());
   cudaFuncSetAttribute(dgemm_nt_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgemm_smem_bytes<64>());
+  { int dev = 0, v = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (v > 2048) CK(cudaFuncSetAttribute(dgemm_nt_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v - 1024)); }   // static shared memory counts too
   cudaFuncSetAttribute(potf2_inv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 64 * 65 * sizeof(double)));
   // the staged m-vector of tri_gemv / the row-split of cols_dot exceed the 48 KB default for m > 6144
   CK(cudaFuncSetAttribute(tri_gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(mm * sizeof(double), 1024)));

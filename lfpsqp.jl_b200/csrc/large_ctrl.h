@@ -15,6 +15,7 @@ struct LargeCtrl {
   int pcg_iter, pcg_lim, pcg_status;  // pcg: 0 running, 1 converged (norm_res<=tol), 4 limit
   int rankflag, commfail;    // rankflag: Cholesky pivot below the rank threshold ; commfail: a peer-memory exchange timed out
   double ldiag_min, ldiag_max;   // explicit-inverse guard (large.cu::factorize): estimate of lambda_min(G), trace(G)
+  unsigned long long nz_count;   // non-zero entries of the zero-slab map of J (large_gemm.cuh::zero_slab_map_kernel)
 };
 
 // Peer-memory region every rank exports over CUDA IPC (comm.cu).  First part: pull-model all-reduce kernels of comm.cu

@@ -23,6 +23,10 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool pr
   int sz = pred ? 16 : 0;  // src-size 0 => zero-fill
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
 }
+__device__ __forceinline__ void cp_async16_sz(void *smem, const void *gmem, int sz) {   // sz in {0, 8, 16}: the rest is zero-filled
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
@@ -31,15 +35,31 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// Optional extras of one GEMM launch (all off by default).
+//   batch > 1 : blockIdx.z selects one of `batch` independent products of identical shape (element strides batch_a/b/c);
+//               used by the recursive triangular inverse, excludes split-K
+//   tri bit 0 : A is upper triangular (row i is zero for k < i)  -> the K loop of a tile starts at its first row
+//   tri bit 1 : B is lower triangular (row j is zero for k > j)  -> the K loop of a tile ends at its last row of B
+//   nz        : zero-slab map of A and B (SKIP instantiation, SYRK of one matrix): nz[rb * nz_ld + kc] != 0 iff the 64-row block
+//               rb has a non-zero in its K chunk kc (GM_BK columns); a K chunk is skipped when the A rows or the B rows of the
+//               tile are all zero there (adds only +0.0 terms: the result is bit-identical unless the other operand holds Inf/NaN)
+struct GemmExt {
+  int64_t batch_a = 0, batch_b = 0, batch_c = 0;
+  int batch = 1, tri = 0;
+  const unsigned char *nz = nullptr;
+  int64_t nz_ld = 0;
+  int nz_rows = 0;
+};
+
 // C (op)= A * B'.  BN in {128, 64}.  256 threads = 8 warps as 2 (M) x 4 (N): warp tile 64 x (BN/4).
 // lower_only: skip tiles strictly above the diagonal (SYRK / symmetric trailing update); tile (bi,bj) kept iff bi*BM+BM > bj*BN.
 // ksplit > 1: split-K, slice z writes its partial into C + z*c_split_stride (ASSIGN only); the caller reduces.
 // Requirements: lda, ldb even; A, B 16-byte aligned; K arbitrary (zero-filled), M, N arbitrary (predicated).
-template <int BN>
+template <int BN, bool SKIP = false>
 __global__ void __launch_bounds__(256) dgemm_nt_kernel(int M, int N, int K, const double *__restrict__ A, int64_t lda,
                                                        const double *__restrict__ B, int64_t ldb, double *__restrict__ C,
                                                        int64_t ldc, int mode, int lower_only, int ksplit,
-                                                       int64_t c_split_stride) {
+                                                       int64_t c_split_stride, const GemmExt X) {
   constexpr int BM = GM_BM, BK = GM_BK, LD = GM_LD, ST = GM_STAGES;
   constexpr int WN = BN / 4;       // warp tile width
   constexpr int NF = WN / 8;       // B fragments per warp per k4 step
@@ -51,11 +71,40 @@ __global__ void __launch_bounds__(256) dgemm_nt_kernel(int M, int N, int K, cons
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp >> 2, wn = warp & 3;   // 2 x 4
   const int row0 = bi * BM, col0 = bj * BN;
+  int zsplit = blockIdx.z;
+  if (X.batch > 1) {
+    A += (int64_t)blockIdx.z * X.batch_a; B += (int64_t)blockIdx.z * X.batch_b; C += (int64_t)blockIdx.z * X.batch_c;
+    zsplit = 0;
+  }
   // K range of this split
   int kchunks = (K + BK - 1) / BK;
   int per = (kchunks + ksplit - 1) / ksplit;
-  int kc0 = blockIdx.z * per, kc1 = min(kchunks, kc0 + per);
-  if (kc0 >= kc1 && ksplit > 1) { kc1 = kc0; }
+  int kc0 = zsplit * per, kc1 = min(kchunks, kc0 + per);
+  if (X.tri & 1) kc0 = max(kc0, row0 / BK);
+  if (X.tri & 2) kc1 = min(kc1, (col0 + BN + BK - 1) / BK);
+  if (kc0 >= kc1) { kc1 = kc0; }
+  // SKIP: ordered list of the K chunks of [kc0, kc1) in which both the A rows and the B rows of this tile have non-zeros
+  int *klist = reinterpret_cast<int *>(gsm + (size_t)ST * (BM + BN) * LD);
+  int nlist = 0;
+  if (SKIP) {
+    __shared__ int wcnt[8];
+    const int rba = row0 / 64, rbb = col0 / 64;
+    const unsigned char *ma0 = X.nz + (int64_t)rba * X.nz_ld, *ma1 = X.nz + (int64_t)min(rba + 1, X.nz_rows - 1) * X.nz_ld;
+    const unsigned char *mb0 = X.nz + (int64_t)rbb * X.nz_ld, *mb1 = X.nz + (int64_t)min(rbb + (BN > 64 ? 1 : 0), X.nz_rows - 1) * X.nz_ld;
+    for (int base = kc0; base < kc1; base += 256) {
+      const int kc = base + (int)threadIdx.x;
+      const bool f = kc < kc1 && (ma0[kc] | ma1[kc]) && (mb0[kc] | mb1[kc]);
+      const unsigned bal = __ballot_sync(0xffffffffu, f);
+      if ((threadIdx.x & 31) == 0) wcnt[threadIdx.x >> 5] = __popc(bal);
+      __syncthreads();
+      int off = nlist, tot = 0;
+#pragma unroll
+      for (int w = 0; w < 8; w++) { const int cw = wcnt[w]; if (w < (int)(threadIdx.x >> 5)) off += cw; tot += cw; }
+      if (f) klist[off + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u))] = kc;
+      nlist += tot;
+      __syncthreads();
+    }
+  }
   double acc[8][NF][2];
 #pragma unroll
   for (int i = 0; i < 8; i++)
@@ -71,7 +120,7 @@ __global__ void __launch_bounds__(256) dgemm_nt_kernel(int M, int N, int K, cons
       int gr = row0 + r, gk = k0 + ch * 2;
       bool ok = (gr < M) && (gk < K);
       const double *src = ok ? (A + (int64_t)gr * lda + gk) : A;
-      cp_async16(As + ((size_t)stage * BM + r) * LD + ch * 2, src, ok);
+      cp_async16_sz(As + ((size_t)stage * BM + r) * LD + ch * 2, src, ok ? (gk + 1 < K ? 16 : 8) : 0);   // odd K: never read column K
     }
 #pragma unroll
     for (int q = 0; q < (BN * 8) / 256; q++) {
@@ -79,13 +128,13 @@ __global__ void __launch_bounds__(256) dgemm_nt_kernel(int M, int N, int K, cons
       int gr = col0 + r, gk = k0 + ch * 2;
       bool ok = (gr < N) && (gk < K);
       const double *src = ok ? (B + (int64_t)gr * ldb + gk) : B;
-      cp_async16(Bs + ((size_t)stage * BN + r) * LD + ch * 2, src, ok);
+      cp_async16_sz(Bs + ((size_t)stage * BN + r) * LD + ch * 2, src, ok ? (gk + 1 < K ? 16 : 8) : 0);
     }
   };
 
-  const int nk = kc1 - kc0;
+  const int nk = SKIP ? nlist : kc1 - kc0;
   for (int s = 0; s < ST - 1; s++) {
-    if (s < nk) load_stage(s, kc0 + s);
+    if (s < nk) load_stage(s, SKIP ? klist[s] : kc0 + s);
     cp_async_commit();
   }
   for (int it = 0; it < nk; it++) {
@@ -93,7 +142,7 @@ __global__ void __launch_bounds__(256) dgemm_nt_kernel(int M, int N, int K, cons
     __syncthreads();
     {  // prefetch stage it+ST-1 (its buffer was consumed in iteration it-1)
       int nx = it + ST - 1;
-      if (nx < nk) load_stage(nx % ST, kc0 + nx);
+      if (nx < nk) load_stage(nx % ST, SKIP ? klist[nx] : kc0 + nx);
       cp_async_commit();
     }
     const double *as = As + (size_t)(it % ST) * BM * LD + (size_t)(wm * 64) * LD;
@@ -113,7 +162,7 @@ __global__ void __launch_bounds__(256) dgemm_nt_kernel(int M, int N, int K, cons
   }
   cp_async_wait<0>();
   // epilogue: thread holds C[row = lane/4][col = 2*(lane%4) + {0,1}] of each 8x8 atom
-  double *Cz = C + (int64_t)blockIdx.z * c_split_stride;
+  double *Cz = C + (int64_t)zsplit * c_split_stride;
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     int r = row0 + wm * 64 + i * 8 + (lane >> 2);
@@ -138,6 +187,44 @@ __global__ void __launch_bounds__(256) dgemm_nt_kernel(int M, int N, int K, cons
 }
 
 template <int BN> constexpr size_t dgemm_smem_bytes() { return (size_t)GM_STAGES * (GM_BM + BN) * GM_LD * sizeof(double); }
+
+// Zero-slab map of a row-major matrix (rows x cols, ld): nz[rb * nz_ld + kc] = 1 iff rows [64 rb, 64 rb + 64) hold a non-zero
+// (or NaN) in columns [GM_BK kc, GM_BK kc + GM_BK).  One pass over the matrix at HBM speed; grid (ceil(cols / 1024), ceil(rows / 64)).
+// count[0] += number of non-zero map entries (the host reads the density with the control block).
+__global__ void __launch_bounds__(256) zero_slab_map_kernel(const double *__restrict__ A, int64_t ld, int rows, int64_t cols,
+                                                            unsigned char *__restrict__ nz, int64_t nz_ld, unsigned long long *count) {
+  __shared__ int flag[64];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < 64) flag[tid] = 0;
+  __syncthreads();
+  const int r0 = blockIdx.y * 64;
+  const int64_t c0 = (int64_t)blockIdx.x * 1024;
+  unsigned mine = 0;   // bit s: chunk 4 s + lane / 8 of this CTA's 64 chunks
+  for (int rr = warp; rr < 64; rr += 8) {
+    const int r = r0 + rr;
+    if (r >= rows) break;
+    const double *row = A + (int64_t)r * ld + c0;
+#pragma unroll 4
+    for (int s = 0; s < 16; s++) {
+      const int64_t c = (int64_t)s * 64 + 2 * lane;
+      if (c0 + c + 1 < cols) {
+        const double2 v = *reinterpret_cast<const double2 *>(row + c);
+        if (v.x != 0.0 || v.y != 0.0) mine |= 1u << s;
+      } else if (c0 + c < cols) {
+        if (row[c] != 0.0) mine |= 1u << s;
+      }
+    }
+  }
+  for (int s = 0; s < 16; s++) if (mine >> s & 1u) flag[4 * s + (lane >> 3)] = 1;
+  __syncthreads();
+  if (tid < 64) {
+    const int64_t kc = (int64_t)blockIdx.x * 64 + tid;
+    const int f = flag[tid];
+    if (kc < nz_ld) nz[(int64_t)blockIdx.y * nz_ld + kc] = (unsigned char)f;
+    const unsigned bal = __ballot_sync(0xffffffffu, f != 0);
+    if (lane == 0 && bal) atomicAdd(count, (unsigned long long)__popc(bal));
+  }
+}
 
 // ------------------------------------------------------------------ diagonal block: in-shared-memory Cholesky + inverse
 // One CTA (256 threads as a 16 x 16 grid, each owning a 4 x 4 register tile) factors the 64 x 64 diagonal block of A
@@ -176,7 +263,7 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double *A, int64_t lda, 
     __syncthreads();
     double piv = colbuf[k];
     if (!(piv > thresh)) { if (tid == 0 && k < nb_act) flag[0] = 1; piv = (piv > 0.0) ? piv : 1.0; }
-    const double d = sqrt(piv), dinv = 1.0 / d;
+    const double d = sqrt(piv), dinv = 1.0 / d;   // correctly rounded on purpose: rsqrt-based pivots (1-2 ulp) moved bound-active solves by 1e-7
     double lr[4], lc[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) { int gr = 4 * ty + r; lr[r] = (gr > k) ? colbuf[gr] * dinv : 0.0; }
@@ -251,8 +338,9 @@ __global__ void __launch_bounds__(256) diag_thresh_kernel(const double *G, int64
 
 // dst (cols x rows, ldd) = src (rows x cols, lds)'  -- 32x32 tiles through shared memory
 __global__ void __launch_bounds__(256) transpose_kernel(const double *__restrict__ src, int64_t lds, double *__restrict__ dst,
-                                                        int64_t ldd, int rows, int cols) {
+                                                        int64_t ldd, int rows, int cols, int64_t batch_src = 0, int64_t batch_dst = 0) {
   __shared__ double t[32][33];
+  src += (int64_t)blockIdx.z * batch_src; dst += (int64_t)blockIdx.z * batch_dst;
   int bx = blockIdx.x * 32, by = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int r = ty; r < 32; r += 8) {
     int gr = by + r, gc = bx + tx;
@@ -278,6 +366,19 @@ __global__ void copy_block_T_kernel(const double *src, int NB, int nb_act, doubl
   if (e >= NB * NB) return;
   int r = e / NB, c = e % NB;
   if (r < nb_act && c < nb_act) dst[(int64_t)c * ldd + r] = src[e];
+}
+// level 0 of the recursive triangular inverse: diagonal block b of XT = D_b', of Linv = D_b (D_b = L_bb^-1, NB x NB, zero-padded)
+__global__ void __launch_bounds__(256) diag_blocks_kernel(const double *Dblk, int NB, int m, double *XT, double *Linv, int64_t ld) {
+  const int b = blockIdx.x, i0 = b * NB, nb = min(NB, m - i0);
+  const double *D = Dblk + (size_t)b * NB * NB;
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+    const int r = e / NB, c = e % NB;
+    if (r < nb && c < nb) {
+      const double v = D[e];
+      Linv[(int64_t)(i0 + r) * ld + i0 + c] = v;
+      XT[(int64_t)(i0 + c) * ld + i0 + r] = v;
+    }
+  }
 }
 
 }  // namespace lfpsqp

@@ -48,6 +48,13 @@ struct LargeState {
   double *J = nullptr, *G = nullptr, *XT = nullptr, *Linv = nullptr, *Dblk = nullptr, *tmp64 = nullptr, *thresh = nullptr,
          *gemm_ws = nullptr, *Dnr = nullptr, *pairws = nullptr;
   size_t gemm_ws_bytes = 0;
+  // zero-slab map of J for the Gram (large_gemm.cuh): J is stored dense, but the SYRK skips K chunks in which the rows of a tile
+  // are all zero.  gram_mode 0: not decided (scan + skipping kernel, density read with the next control block), 1: block-sparse
+  // (keep scanning: values may change), 2: dense (plain kernel, no scan; sticky -- zeros appearing later only cost time)
+  unsigned char *nzmap = nullptr;
+  int64_t nz_ld = 0;
+  int nz_rows = 0, gram_mode = 0, max_dyn_smem = 48 * 1024;
+  bool nz_pending = false;
   // n_loc vectors
   double *x = nullptr, *xnew = nullptr, *xtil = nullptr, *g = nullptr, *d = nullptr, *nd = nullptr, *w0 = nullptr,
          *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr, *hdiag = nullptr, *ex[4] = {nullptr, nullptr, nullptr, nullptr};
