@@ -91,7 +91,7 @@ static void gemm_nt(LargeState &S, int M, int N, int K, const double *A, int64_t
   }
   if (mode != GEMM_SUB && tiles * 2 <= S.sm_count && K >= 1024 && !X.tri) {
     ksplit = std::min(std::min(16, S.sm_count / tiles), K / 256);
-    while (ksplit > 1 && (size_t)ksplit * M * N * 8 > S.gemm_ws_bytes) ksplit--;
+    while (ksplit > 1 && (size_t)ksplit * M * (N + 1) * 8 > S.gemm_ws_bytes) ksplit--;
     if (ksplit < 1) ksplit = 1;
   } else if (mode == GEMM_ASSIGN && lower && K >= 8192 && tiles < S.sm_count) {
     // wave quantisation of a SYRK that does not fill one wave (C5: 136 lower tiles on 148 SMs = 92 %): split K so that
@@ -100,7 +100,7 @@ static void gemm_nt(LargeState &S, int M, int N, int K, const double *A, int64_t
     auto eff = [&](int ks) { int64_t w = (int64_t)tiles * ks; return (double)w / (double)(((w + S.sm_count - 1) / S.sm_count) * S.sm_count); };
     int best = 1;
     for (int ks = 2; ks <= 16; ks++) {
-      if ((size_t)ks * M * N * 8 > S.gemm_ws_bytes || K / ks < 2048) break;
+      if ((size_t)ks * M * (N + 1) * 8 > S.gemm_ws_bytes || K / ks < 2048) break;
       if (eff(ks) > eff(best) + 0.02) best = ks;
     }
     ksplit = best;
@@ -116,16 +116,18 @@ static void gemm_nt(LargeState &S, int M, int N, int K, const double *A, int64_t
     S.launches++;
   } else {
     grid.z = ksplit;
-    const int64_t stride = (int64_t)M * N;
-    if (skip) dgemm_nt_kernel<128, true><<<grid, 256, skip_smem, S.stream>>>(M, N, K, A, lda, B, ldb, S.gemm_ws, N, GEMM_ASSIGN, lower, ksplit, stride, X);
-    else if (narrow) dgemm_nt_kernel<64><<<grid, 256, dgemm_smem_bytes<64>(), S.stream>>>(M, N, K, A, lda, B, ldb, S.gemm_ws, N, GEMM_ASSIGN, lower, ksplit, stride, X);
-    else dgemm_nt_kernel<128><<<grid, 256, dgemm_smem_bytes<128>(), S.stream>>>(M, N, K, A, lda, B, ldb, S.gemm_ws, N, GEMM_ASSIGN, lower, ksplit, stride, X);
+    const int64_t ldw = (N + 1) & ~1;   // even row pitch: the epilogue stores 16-byte pairs
+    const int64_t stride = (int64_t)M * ldw;
+    if (skip) dgemm_nt_kernel<128, true><<<grid, 256, skip_smem, S.stream>>>(M, N, K, A, lda, B, ldb, S.gemm_ws, ldw, GEMM_ASSIGN, lower, ksplit, stride, X);
+    else if (narrow) dgemm_nt_kernel<64><<<grid, 256, dgemm_smem_bytes<64>(), S.stream>>>(M, N, K, A, lda, B, ldb, S.gemm_ws, ldw, GEMM_ASSIGN, lower, ksplit, stride, X);
+    else dgemm_nt_kernel<128><<<grid, 256, dgemm_smem_bytes<128>(), S.stream>>>(M, N, K, A, lda, B, ldb, S.gemm_ws, ldw, GEMM_ASSIGN, lower, ksplit, stride, X);
     const double *ws = S.gemm_ws;
     const double sgn = (mode == GEMM_ASSIGN_NEG) ? -1.0 : 1.0;
     const int lo = lower;
-    vec(S, stride, [=] __device__(int64_t e, double *) {
-      int r = (int)(e / N), cc = (int)(e % N);
+    vec(S, (int64_t)M * N, [=] __device__(int64_t e0, double *) {
+      int r = (int)(e0 / N), cc = (int)(e0 % N);
       if (lo && (r / GM_BM) * GM_BM + GM_BM <= (cc / BN) * BN) return;   // tile was skipped
+      const int64_t e = (int64_t)r * ldw + cc;
       double s = 0.0;
       for (int z = 0; z < ksplit; z++) s += ws[(int64_t)z * stride + e];
       C[(int64_t)r * ldc + cc] = sgn * s;
@@ -338,7 +340,8 @@ template <class T> static bool dalloc(LargeState &S, T **p, size_t count);
 static void gram_syrk(LargeState &S, const double *Jg) {
   const int m = S.m;
   GemmExt X; const GemmExt *ext = nullptr;
-  if (S.gram_mode != 2 && S.nzmap && m > 64) {
+  const char *env = getenv("LFPSQP_GRAM_SKIP");   // "0": always the plain dense SYRK (tests compare the two bit for bit)
+  if (S.gram_mode != 2 && S.nzmap && m > 64 && !(env && env[0] == '0')) {
     cudaMemsetAsync(&S.ctrl->nz_count, 0, sizeof(unsigned long long), S.stream);
     dim3 sg((unsigned)((S.n_loc + 1023) / 1024), (unsigned)S.nz_rows);
     zero_slab_map_kernel<<<sg, 256, 0, S.stream>>>(Jg, S.ldj, m, S.n_loc, S.nzmap, S.nz_ld, &S.ctrl->nz_count);

@@ -17,7 +17,7 @@ def rel(a, b):
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
 
 
-@pytest.mark.parametrize("n,m", [(512, 32), (1000, 130), (4096, 200), (2048, 64), (770, 1)])
+@pytest.mark.parametrize("n,m", [(512, 32), (1000, 130), (4096, 200), (2048, 64), (770, 1), (1200, 193), (1500, 321), (2048, 576), (1100, 65)])
 def test_factor_and_projection_vs_numpy(L, n, m):
     # ksvd! replacement (la_helper.jl:8-34): G = J J', L = chol(G), L^-1 ; kgemv! pair (optimize.jl:306-307) ; multipliers (:333-343)
     Q, A, b, xt, w, x0 = L.make_diagquad(n, m, seed=n + m, cond=100.0)
@@ -376,3 +376,33 @@ def test_rank_deficient_jacobian_large_mode_vs_oracle(L, oracle):
     print(parity.fmt_record(rec), "lam err", rel(lmb, runs["base"][3][0]))
     assert rec["failures"] == 0, parity.fmt_record(rec)
     assert np.max(np.abs(0.5 * Q @ (x * x) + A @ x - b)) < 1e-6               # feasible to eps_c
+
+
+def test_zero_slab_skipping_gram_is_bit_identical(L, monkeypatch):
+    # The Gram of a block-sparse J (stored dense) skips all-zero (64 rows x 16 columns) slabs: same bits as the plain dense SYRK,
+    # for Thomson (rows touch 3 columns) and for a DIAGQUAD whose Q, A carry a banded pattern; a dense J takes the plain kernel
+    # after the first factorisation (density read with the control block) and must give the same bits as well.
+    rng = np.random.default_rng(12)
+    npts = 300
+    x0 = rng.standard_normal((npts, 3)); x0 /= np.linalg.norm(x0, axis=1, keepdims=True); x0 = x0.ravel()
+    n, m = 3072, 200
+    Q, A, b, xt, w, xq = L.make_diagquad(n, m, seed=4, cond=50.0)
+    band = np.zeros((m, n), dtype=bool)
+    for i in range(m):
+        lo = (i * 13) % (n - 200); band[i, lo:lo + 150] = True
+    Qb, Ab = np.where(band, Q, 0.0), np.where(band, A, 0.0)
+    cases = [("thomson", lambda: L.LargeProblem(L.families.thomson(npts)), x0),
+             ("banded diagquad", lambda: L.LargeProblem(L.families.diagquad(Qb, Ab, b, xt, w)), xq),
+             ("dense diagquad", lambda: L.LargeProblem(L.families.diagquad(Q, A, b, xt, w)), xq)]
+    for name, make, xs in cases:
+        monkeypatch.setenv("LFPSQP_GRAM_SKIP", "0")
+        ref = make().factor(xs)
+        monkeypatch.delenv("LFPSQP_GRAM_SKIP")
+        P = make()
+        for rep in range(2):       # second call: after the density verdict
+            fac = P.factor(xs)
+            for key in ("G", "L", "Linv"):
+                assert np.array_equal(np.tril(fac[key]), np.tril(ref[key])), (name, rep, key)
+    J = Qb * xq[None, :] + Ab
+    assert rel(np.tril(fac["G"]), np.tril((Q * xq[None, :] + A) @ (Q * xq[None, :] + A).T)) < 1e-14
+    assert J.shape == (m, n)
