@@ -221,7 +221,10 @@ def large_n_section(L, ctx, torch, dev, with_cpu, dist=None, rank=0, world=1, we
         out["gram"] = {"kernel": "dgemm_nt_kernel<128> (SYRK, lower tiles, mma.sync.m8n8k4.f64)", "ms": gram_ms, "flops": flops,
                        "bound": "tensor", "achieved": flops / (gram_ms * 1e-3) / 1e12, "peak": dmma, "unit": "TFLOP/s",
                        "frac": flops / (gram_ms * 1e-3) / 1e12 / dmma,
-                       "peak_source": "DMMA (mma.sync.m8n8k4.f64) microbenchmark measured in this run"}
+                       "peak_source": "DMMA (mma.sync.m8n8k4.f64) microbenchmark measured in this run",
+                       "peak_method": "lfpsqp_bench_fp64_peak(which=1), csrc/microbench.cu: 148*8 CTAs x 256 threads, 4096 iterations of "
+                                      "32 register-only mma.sync.m8n8k4.f64 per warp (4 independent accumulator pairs), 512 flops "
+                                      "per instruction per warp, CUDA-event timed, best of 3 after one warm-up"}
     except Exception as e:  # noqa
         out["gram"] = {"error": str(e)}
     if with_cpu:
@@ -581,6 +584,9 @@ def main():
                 "achieved": ach_tf, "peak": dfma, "unit": "TFLOP/s", "frac": ach_tf / dfma,
                 "traffic": _traffic("batched_reg_kernel", "bytes_per_launch"), "kernel_ms": kms,
                 "flops_per_instance": flops, "peak_source": "DFMA microbenchmark measured in this run (lfpsqp_bench_fp64_peak)",
+                "peak_method": "lfpsqp_bench_fp64_peak(which=0), csrc/microbench.cu: 148*8 CTAs x 256 threads, 4096 iterations of 64 "
+                               "DFMA per thread in 8 independent chains, 2 flops per DFMA, CUDA-event timed, best of 3 after one "
+                               "warm-up; flops_per_instance = the oracle's instrumented FP64 operation count (mean of 4096 instances)",
                 "hbm": hbm_roof}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),

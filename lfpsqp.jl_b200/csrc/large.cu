@@ -444,11 +444,12 @@ static int factorize(lfpsqp_ctx *c, LargeState &S) {
       if (np <= 0) continue;
       const int o = part == 0 ? 0 : o_r, B2 = part == 0 ? B : B2r;
       const int64_t pstride = (int64_t)2 * B * ldm + 2 * B;
-      double *Tt = S.gemm_ws;                             // B x B2 per pair, ld B
-      GemmExt e1; e1.batch = np; e1.batch_a = pstride; e1.batch_b = pstride; e1.batch_c = (int64_t)B * B; e1.tri = 1;
-      gemm_nt(S, B, B2, B, S.XT + (int64_t)o * ldm + o, ldm, S.G + (int64_t)(o + B) * ldm + o, ldm, Tt, B, GEMM_ASSIGN, 0, &e1);
-      GemmExt e2; e2.batch = np; e2.batch_a = (int64_t)B * B; e2.batch_b = pstride; e2.batch_c = pstride; e2.tri = 2;
-      gemm_nt(S, B, B2, B2, Tt, B, S.Linv + (int64_t)(o + B) * ldm + (o + B), ldm, S.XT + (int64_t)o * ldm + (o + B), ldm, GEMM_ASSIGN_NEG, 0, &e2);
+      double *Tt = S.gemm_ws;                             // B x B2 per pair; row pitch B + 8: a power-of-two pitch made the
+      const int64_t ldt = B + 8;                          // 128 rows of a tile hit the same L2 slices (second GEMM 1.5x slower)
+      GemmExt e1; e1.batch = np; e1.batch_a = pstride; e1.batch_b = pstride; e1.batch_c = (int64_t)B * ldt; e1.tri = 1;
+      gemm_nt(S, B, B2, B, S.XT + (int64_t)o * ldm + o, ldm, S.G + (int64_t)(o + B) * ldm + o, ldm, Tt, ldt, GEMM_ASSIGN, 0, &e1);
+      GemmExt e2; e2.batch = np; e2.batch_a = (int64_t)B * ldt; e2.batch_b = pstride; e2.batch_c = pstride; e2.tri = 2;
+      gemm_nt(S, B, B2, B2, Tt, ldt, S.Linv + (int64_t)(o + B) * ldm + (o + B), ldm, S.XT + (int64_t)o * ldm + (o + B), ldm, GEMM_ASSIGN_NEG, 0, &e2);
       dim3 tg((B2 + 31) / 32, (B + 31) / 32, np);
       transpose_kernel<<<tg, 256, 0, S.stream>>>(S.XT + (int64_t)o * ldm + (o + B), ldm, S.Linv + (int64_t)(o + B) * ldm + o, ldm, B, B2, pstride, pstride);
       S.launches++;

@@ -66,7 +66,13 @@ __global__ void __launch_bounds__(256) dgemm_nt_kernel(int M, int N, int K, cons
   extern __shared__ double gsm[];
   double *As = gsm;                          // ST x BM x LD
   double *Bs = gsm + (size_t)ST * BM * LD;   // ST x BN x LD
-  const int bi = blockIdx.y, bj = blockIdx.x;
+  // tri bit 1: the K loop grows with the tile column -> walk the grid column by column from the last one, so that CTAs are issued
+  // longest tile first (as the row-major order already does for tri bit 0); a mixed order left a long tile for the last wave
+  int bi = blockIdx.y, bj = blockIdx.x;
+  if (X.tri & 2) {
+    const int t = blockIdx.y * gridDim.x + blockIdx.x;
+    bj = (int)gridDim.x - 1 - t / (int)gridDim.y; bi = t % (int)gridDim.y;
+  }
   if (lower_only && (bi * BM + BM <= bj * BN)) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp >> 2, wn = warp & 3;   // 2 x 4
