@@ -202,6 +202,8 @@ int launch_warp(lfpsqp_ctx *c, BatchedArgs &A, int use_nr) {
   }
   if (resident < 1) return c->fail(LFPSQP_ERR_CUDA, "batched_warp_kernel cannot be made resident");
   const size_t smem = bnd_bytes + warps * per_warp;
+  c->round_instances = (int64_t)c->sm_count * resident * warps;
+  if (c->query_round) return LFPSQP_OK;
   int64_t grid = (int64_t)c->sm_count * resident;
   int64_t need = (A.B + warps - 1) / warps;
   if (grid > need) grid = need;
@@ -222,6 +224,8 @@ template <class Fam, int NT>
 int launch_tiny(lfpsqp_ctx *c, BatchedArgs &A) {
   const int threads = 128;
   int64_t grid = (A.B + threads - 1) / threads;
+  c->round_instances = 0;   // one thread per instance, not persistent: no round structure
+  if (c->query_round) return LFPSQP_OK;
   cudaEventRecord(c->ev0, c->stream);
   batched_tiny_kernel<Fam, NT><<<(unsigned)grid, threads, 0, c->stream>>>(A);
   cudaEventRecord(c->ev1, c->stream);
@@ -360,6 +364,45 @@ extern "C" int lfpsqp_solve_batched(lfpsqp_ctx *c, int family, int64_t n, int64_
   // chunking: keep every chunk big enough to fill the GPU several times over
   int nchunk = 1;
   if (B >= 16384) nchunk = (int)std::min<int64_t>(8, B / 8192);
+  // pipeline shape: the first chunk's H2D and the last chunk's D2H are the only copies the kernels cannot hide, so those two
+  // chunks are half the size of the others (measured at C2, 65,536 instances: 8 equal chunks 2.050 ms, halved ends 2.009 ms,
+  // 16 chunks 2.06-2.09 ms, 4 chunks 2.24 ms; device-resident kernel 1.74 ms).  LFPSQP_PIPE_CHUNKS / LFPSQP_PIPE_RAMP override
+  // (tools/e2e_pipe.py).  LFPSQP_PIPE_ROUNDS=1 cuts the chunks in whole rounds of the persistent kernels (resident CTAs x
+  // instances per CTA) instead: measured SLOWER (2.11 ms) -- a partly filled last round costs nothing, because the idle CTAs
+  // exit and the next chunk's CTAs take their place, while whole rounds end all CTAs at once and expose the launch gap.
+  double ramp = 0.5;
+  bool shaped = true;
+  if (const char *e = getenv("LFPSQP_PIPE_ROUNDS")) shaped = !(e[0] == '1');
+  if (const char *e = getenv("LFPSQP_PIPE_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 64 && B >= 2 * v) { nchunk = v; shaped = true; } }
+  if (const char *e = getenv("LFPSQP_PIPE_RAMP")) { double v = atof(e); if (v > 0.05 && v <= 1.0) ramp = v; }
+  std::vector<int64_t> cut(nchunk + 1, 0);
+  int64_t q = 0;
+  if (nchunk > 1 && !shaped) {
+    BatchedArgs Aq = A0; Aq.B = B;
+    c->query_round = 1; c->round_instances = 0;
+    const int qrc = dispatch_batched(c, Aq);
+    c->query_round = 0;
+    if (qrc == LFPSQP_OK) q = c->round_instances;
+  }
+  if (q > 0 && B >= 4 * q) {
+    const int64_t R = B / q, rem = B - R * q;
+    int64_t mid = 2 * q;
+    while ((R - 1 + mid / q - 1) / (mid / q) > 12) mid += 2 * q;   // at most 12 middle chunks
+    std::vector<int64_t> c2; c2.push_back(0); c2.push_back(q);
+    int64_t left = (R - 1) * q;
+    while (left > 0) { const int64_t t = std::min(mid, left); c2.push_back(c2.back() + t); left -= t; }
+    if (rem > 0) c2.push_back(B);
+    cut = c2; nchunk = (int)cut.size() - 1;
+  } else {
+    const double tot = (nchunk > 2) ? (nchunk - 2) + 2 * ramp : (double)nchunk;
+    double acc = 0;
+    for (int ci = 0; ci < nchunk; ci++) {
+      acc += (nchunk > 2 && (ci == 0 || ci == nchunk - 1)) ? ramp : 1.0;
+      cut[ci + 1] = std::min<int64_t>(B, (int64_t)(B * (acc / tot) + 0.5));
+    }
+    cut[nchunk] = B;
+    for (int ci = 0; ci < nchunk; ci++) if (cut[ci + 1] <= cut[ci]) { nchunk = 1; cut.assign(2, 0); cut[1] = B; break; }
+  }
   const int NS = 3;
   if (nchunk > 1 && !c->pipe[0]) {
     for (int i = 0; i < NS; i++) if (cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); nchunk = 1; break; }
@@ -371,7 +414,7 @@ extern "C" int lfpsqp_solve_batched(lfpsqp_ctx *c, int family, int64_t n, int64_
   c->last_launches = 0;
   int64_t launches = 0;
   for (int ci = 0; ci < nchunk && rc == 0; ci++) {
-    const int64_t lo = B * ci / nchunk, hi = B * (ci + 1) / nchunk, nb = hi - lo;
+    const int64_t lo = cut[ci], hi = cut[ci + 1], nb = hi - lo;
     cudaStream_t s = (nchunk > 1) ? c->pipe[ci % NS] : user_stream;
     if (npar && fam_stride) cudaMemcpyAsync(d_par + lo * fam_stride, fam_params + lo * fam_stride, (size_t)nb * fam_stride * 8, cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(d_x0 + lo * n, x0 + lo * n, (size_t)n * nb * 8, cudaMemcpyHostToDevice, s);
@@ -385,7 +428,7 @@ extern "C" int lfpsqp_solve_batched(lfpsqp_ctx *c, int family, int64_t n, int64_
     A.fam_params = npar ? (fam_stride ? d_par + lo * fam_stride : d_par) : nullptr; A.fam_stride = fam_stride;
     A.x0 = d_x0 + lo * n; A.x_out = d_x + lo * n; A.obj_hist = d_obj + lo * H; A.obj_len = d_len + lo;
     A.lambda = d_lam + lo * ME; A.term = d_term + lo; A.stats = d_stats ? d_stats + lo : nullptr;
-    c->stream = s; c->work_counter = counter0 + (ci % 8);
+    c->stream = s; c->work_counter = counter0 + (ci % 32);   // 256 B = 32 counters: one per chunk in flight
     rc = dispatch_batched(c, A);
     launches += c->last_launches;
     if (rc) break;

@@ -18,6 +18,8 @@ int launch(lfpsqp_ctx *c, BatchedArgs &A) {
   int resident = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, NT, smem);
   if (e != cudaSuccess || resident < 1) return c->cuda_fail(e, "occupancy query (batched_reg_kernel)");
+  c->round_instances = (int64_t)c->sm_count * resident * GROUPS;
+  if (c->query_round) return LFPSQP_OK;
   int64_t grid = (int64_t)c->sm_count * resident, need = (A.B + GROUPS - 1) / GROUPS;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;

@@ -28,6 +28,10 @@ struct lfpsqp_ctx {
   double last_ms = 0.0;
   int64_t last_launches = 0;
   int last_cfg_warps = 0, last_cfg_grid = 0, last_cfg_smem = 0, last_cfg_resident = 0;
+  // persistent batched kernels work in ROUNDS of round_instances = resident CTAs x instances per CTA; query_round = 1 makes
+  // the launchers fill it in and return without launching (the host pipeline sizes its chunks in whole rounds)
+  int query_round = 0;
+  int64_t round_instances = 0;
   std::string err;
   std::vector<void *> bufs;  // grow-only device arena, one slot per role (no allocation inside solve loops)
   std::vector<size_t> caps;
