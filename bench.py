@@ -391,6 +391,20 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_cpus(gpu_index):
+    """N ranks x 90 MB of pinned traffic per step: keep every rank's host buffers and its calling thread on the CPU socket its
+    GPU hangs off (NVML's ideal CPU affinity), so that the copies do not cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return {"method": "nvmlDeviceSetCpuAffinity", "cpus_before": before, "cpus": len(os.sched_getaffinity(0))}
+    except Exception as e:  # noqa
+        return {"method": "none", "error": repr(e)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -399,6 +413,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-large", action="store_true", help="skip the secondary large-n (C5) section")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not bind each rank to the CPUs next to its GPU (A/B)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -416,6 +431,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dist = None
+    host_placement = None
+    if world > 1 and not args.no_numa_bind:
+        host_placement = bind_to_gpu_cpus(local_rank)   # before the pinned buffers are allocated (first touch = local node)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -598,7 +616,7 @@ def main():
                        "l2": "256 MiB buffer written between timed iterations (flush not timed)",
                        "parallelism": "instances sharded over %d GPU(s), no collective" % world},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "modes": e2e_modes,
+                    "modes": e2e_modes, "host_placement": host_placement,
                     "note": "bytes are per GPU per step; value = best of the listed ways to drive N GPUs through the C ABI "
                             "(one process per GPU, or one host call on a multi-GPU context)"},
             "gpu_launches": int(K), "clocks": clocks, "roofline": roofline}
