@@ -400,6 +400,20 @@ static int factorize(lfpsqp_ctx *c, LargeState &S) {
   constexpr int NB = 64;
   const size_t psm = 2 * NB * (NB + 1) * sizeof(double);
   int nblk = (m + NB - 1) / NB;
+  // Block structure of G (and, with fill-in, of L): panel / trailing / inverse GEMM tiles whose operands are structurally zero
+  // return at once.  A dense G costs one 15 us scan; a block-sparse one (Thomson: G is diagonal) keeps only the potf2 chain.
+  GemmExt F1, F2, F3;
+  const GemmExt *f1 = nullptr, *f2 = nullptr;
+  {
+    const char *env = getenv("LFPSQP_GRAM_SKIP");
+    if (S.blkflag && nblk > 1 && !(env && env[0] == '0')) {
+      block_nz_kernel<<<dim3(nblk, nblk), 256, 0, S.stream>>>(S.G, ldm, m, S.blkflag, nblk);
+      S.launches++;
+      F1.bf = S.blkflag; F1.bf_ld = nblk; F1.bf_n = nblk; F1.bf_mode = 1;
+      F2 = F1; F2.bf_mode = 2; F3 = F1; F3.bf_mode = 3;
+      f1 = &F1; f2 = &F2;
+    }
+  }
   // Right-looking blocked Cholesky with LOOK-AHEAD: the single-CTA factorisation of diagonal block b+1 (latency-bound, ~50 us)
   // runs on a second stream while the main stream applies the rank-NB update of block b to the rest of the trailing matrix.
   // Per block: potf2(b) -> L21 = A21 D' -> [panel part of the update: the nb2 columns of block b+1] -> event -> potf2(b+1) on
@@ -417,15 +431,19 @@ static int factorize(lfpsqp_ctx *c, LargeState &S) {
     if (rem <= 0) break;
     double *A21 = S.G + (int64_t)(j0 + nb) * ldm + j0;
     double *A22 = S.G + (int64_t)(j0 + nb) * ldm + (j0 + nb);
-    gemm_nt(S, rem, nb, nb, A21, ldm, Db, NB, A21, ldm, GEMM_ASSIGN, 0);                         // L21 = A21 D'
+    F1.bf_a0 = b + 1; F1.bf_col = b;
+    gemm_nt(S, rem, nb, nb, A21, ldm, Db, NB, A21, ldm, GEMM_ASSIGN, 0, f1);                     // L21 = A21 D'
     const int nb2 = std::min(NB, rem), rem2 = rem - nb2;
-    gemm_nt(S, rem, nb2, nb, A21, ldm, A21, ldm, A22, ldm, GEMM_SUB, 0);                         // panel of block b+1: A22[:, 0:nb2] -= L21 L21[0:nb2]'
+    F2.bf_a0 = b + 1; F2.bf_b0 = b + 1; F2.bf_col = b;
+    gemm_nt(S, rem, nb2, nb, A21, ldm, A21, ldm, A22, ldm, GEMM_SUB, 0, f2);                     // panel of block b+1: A22[:, 0:nb2] -= L21 L21[0:nb2]'
     if (side_s != main_s) { cudaEventRecord(S.ev_panel, main_s); cudaStreamWaitEvent(side_s, S.ev_panel, 0); }
     potf2_inv_kernel<NB><<<1, 256, psm, side_s>>>(A22, ldm, nb2, S.Dblk + (size_t)(b + 1) * NB * NB, S.thresh, &S.ctrl->rankflag);
     S.launches++;
     if (side_s != main_s) cudaEventRecord(S.ev_potf, side_s);
-    if (rem2 > 0)                                                                                // the rest of A22 -= L21 L21' (lower)
-      gemm_nt(S, rem2, rem2, nb, A21 + (int64_t)nb2 * ldm, ldm, A21 + (int64_t)nb2 * ldm, ldm, A22 + (int64_t)nb2 * ldm + nb2, ldm, GEMM_SUB, 1);
+    if (rem2 > 0) {                                                                              // the rest of A22 -= L21 L21' (lower)
+      F2.bf_a0 = b + 2; F2.bf_b0 = b + 2;
+      gemm_nt(S, rem2, rem2, nb, A21 + (int64_t)nb2 * ldm, ldm, A21 + (int64_t)nb2 * ldm, ldm, A22 + (int64_t)nb2 * ldm + nb2, ldm, GEMM_SUB, 1, f2);
+    }
     if (side_s != main_s) cudaStreamWaitEvent(main_s, S.ev_potf, 0);
   }
   // XT = L^-T (upper triangular, row-major) and Linv = L^-1 by recursive doubling from the inverted diagonal blocks:
@@ -446,9 +464,12 @@ static int factorize(lfpsqp_ctx *c, LargeState &S) {
       const int64_t pstride = (int64_t)2 * B * ldm + 2 * B;
       double *Tt = S.gemm_ws;                             // B x B2 per pair; row pitch B + 8: a power-of-two pitch made the
       const int64_t ldt = B + 8;                          // 128 rows of a tile hit the same L2 slices (second GEMM 1.5x slower)
-      GemmExt e1; e1.batch = np; e1.batch_a = pstride; e1.batch_b = pstride; e1.batch_c = (int64_t)B * ldt; e1.tri = 1;
+      GemmExt e1 = f1 ? F3 : GemmExt();                    // a pair whose L21 is structurally zero keeps XT12 = 0 (memset above)
+      if (f1) { e1.bf_r0 = (o + B) / NB; e1.bf_r1 = (o + B + B2 + NB - 1) / NB; e1.bf_c0 = o / NB; e1.bf_c1 = (o + B) / NB; e1.bf_batch = 2 * B / NB; }
+      GemmExt e2 = e1;
+      e1.batch = np; e1.batch_a = pstride; e1.batch_b = pstride; e1.batch_c = (int64_t)B * ldt; e1.tri = 1;
       gemm_nt(S, B, B2, B, S.XT + (int64_t)o * ldm + o, ldm, S.G + (int64_t)(o + B) * ldm + o, ldm, Tt, ldt, GEMM_ASSIGN, 0, &e1);
-      GemmExt e2; e2.batch = np; e2.batch_a = (int64_t)B * ldt; e2.batch_b = pstride; e2.batch_c = pstride; e2.tri = 2;
+      e2.batch = np; e2.batch_a = (int64_t)B * ldt; e2.batch_b = pstride; e2.batch_c = pstride; e2.tri = 2;
       gemm_nt(S, B, B2, B2, Tt, ldt, S.Linv + (int64_t)(o + B) * ldm + (o + B), ldm, S.XT + (int64_t)o * ldm + (o + B), ldm, GEMM_ASSIGN_NEG, 0, &e2);
       dim3 tg((B2 + 31) / 32, (B + 31) / 32, np);
       transpose_kernel<<<tg, 256, 0, S.stream>>>(S.XT + (int64_t)o * ldm + (o + B), ldm, S.Linv + (int64_t)(o + B) * ldm + o, ldm, B, B2, pstride, pstride);
@@ -1119,6 +1140,7 @@ extern "C" int lfpsqp_large_setup(lfpsqp_ctx *c, int family, int64_t n_global, i
   ok &= dalloc(S, &S.Dblk, ((mm + 63) / 64) * 64 * 64); ok &= dalloc(S, &S.tmp64, mm * 64); ok &= dalloc(S, &S.thresh, 8);
   S.nz_rows = (int)((mm + 63) / 64); S.nz_ld = (int64_t)((S.ldj + GM_BK - 1) / GM_BK + 64) / 64 * 64; S.gram_mode = 0; S.nz_pending = false;
   ok &= dalloc(S, &S.nzmap, (size_t)S.nz_rows * S.nz_ld);
+  ok &= dalloc(S, &S.blkflag, (size_t)S.nz_rows * S.nz_rows + 1);
   { int dev = 0, v = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev); if (v > 2048) S.max_dyn_smem = v - 1024; }
   S.gemm_ws_bytes = std::max<size_t>((size_t)16 * mm * 64 * 8, std::min<size_t>(mm * mm * 8 * 16, (size_t)1 << 30));
   { char *ws = nullptr; ok &= dalloc(S, &ws, S.gemm_ws_bytes); S.gemm_ws = (double *)ws; }

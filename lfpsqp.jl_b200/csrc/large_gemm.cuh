@@ -49,6 +49,14 @@ struct GemmExt {
   const unsigned char *nz = nullptr;
   int64_t nz_ld = 0;
   int nz_rows = 0;
+  // block-structure flags of the factorisation (large.cu::factorize): bf[I * bf_ld + J] != 0 iff the 64 x 64 block (I, J), I >= J,
+  // of the working matrix (G, then L) may hold a non-zero.  A tile whose operands are structurally zero returns at once
+  // (its contribution is exactly +0), a computed trailing tile marks its blocks as fill-in.
+  //   bf_mode 1 (L21 = A21 D'):       skip iff the tile's A row blocks are zero in block column bf_col
+  //   bf_mode 2 (C -= A B', A, B rows of L21): skip iff the A row blocks or the B row blocks are zero in column bf_col; else mark
+  //   bf_mode 3 (recursive inverse):  skip iff the whole block range [bf_r0, bf_r1) x [bf_c0, bf_c1) (+ the batch offset) is zero
+  int *bf = nullptr;
+  int bf_ld = 0, bf_n = 0, bf_mode = 0, bf_a0 = 0, bf_b0 = 0, bf_col = 0, bf_r0 = 0, bf_r1 = 0, bf_c0 = 0, bf_c1 = 0, bf_batch = 0;
 };
 
 // C (op)= A * B'.  BN in {128, 64}.  256 threads = 8 warps as 2 (M) x 4 (N): warp tile 64 x (BN/4).
@@ -75,6 +83,29 @@ __global__ void __launch_bounds__(256) dgemm_nt_kernel(int M, int N, int K, cons
   }
   if (lower_only && (bi * BM + BM <= bj * BN)) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (X.bf_mode) {
+    if (X.bf_mode == 3) {
+      const int off = (int)blockIdx.z * X.bf_batch, w = X.bf_c1 - X.bf_c0, cnt = (X.bf_r1 - X.bf_r0) * w;
+      int any = 0;
+      for (int e = tid; e < cnt; e += 256) any |= X.bf[(int64_t)(X.bf_r0 + off + e / w) * X.bf_ld + X.bf_c0 + off + e % w];
+      if (!__syncthreads_or(any)) return;
+    } else {
+      const int ia = X.bf_a0 + (BM / 64) * bi, ib = X.bf_b0 + (BN / 64) * bj;
+      const int fa0 = X.bf[(int64_t)ia * X.bf_ld + X.bf_col], fa1 = (ia + 1 < X.bf_n) ? X.bf[(int64_t)(ia + 1) * X.bf_ld + X.bf_col] : 0;
+      if (!(fa0 | fa1)) return;
+      if (X.bf_mode == 2) {
+        const int fb0 = X.bf[(int64_t)ib * X.bf_ld + X.bf_col];
+        const int fb1 = (BN > 64 && ib + 1 < X.bf_n) ? X.bf[(int64_t)(ib + 1) * X.bf_ld + X.bf_col] : 0;
+        if (!(fb0 | fb1)) return;
+        if (tid == 0) {   // fill-in (block columns > bf_col: nobody reads them during this step)
+          if (fa0 & fb0) X.bf[(int64_t)ia * X.bf_ld + ib] = 1;
+          if (fa1 & fb0) X.bf[(int64_t)(ia + 1) * X.bf_ld + ib] = 1;
+          if (BN > 64 && (fa0 & fb1)) X.bf[(int64_t)ia * X.bf_ld + ib + 1] = 1;
+          if (BN > 64 && (fa1 & fb1)) X.bf[(int64_t)(ia + 1) * X.bf_ld + ib + 1] = 1;
+        }
+      }
+    }
+  }
   const int wm = warp >> 2, wn = warp & 3;   // 2 x 4
   const int row0 = bi * BM, col0 = bj * BN;
   int zsplit = blockIdx.z;
@@ -329,6 +360,22 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double *A, int64_t lda, 
     if (r < nb_act && c < nb_act) A[(int64_t)r * lda + c] = Ls[r][c];
     Dout[e] = (r < nb_act && c < nb_act) ? Ds[r][c] : 0.0;
   }
+}
+
+// bf[I * ld + J] = 1 iff the 64 x 64 block (I, J), I >= J, of the lower triangle of G holds a non-zero (or NaN); grid (nblk, nblk)
+__global__ void __launch_bounds__(256) block_nz_kernel(const double *__restrict__ G, int64_t ldg, int m, int *bf, int ld) {
+  const int I = blockIdx.y, J = blockIdx.x;
+  if (J > I) { if (threadIdx.x == 0) bf[(int64_t)I * ld + J] = 0; return; }
+  int any = 0;
+  for (int e = threadIdx.x; e < 64 * 32; e += 256) {
+    const int r = 64 * I + e / 32, c = 64 * J + 2 * (e % 32);
+    if (r < m && c < m) {
+      const double2 v = *reinterpret_cast<const double2 *>(G + (int64_t)r * ldg + c);   // the pad column (odd m) is never non-zero
+      any |= (v.x != 0.0) | ((c + 1 < m) & (v.y != 0.0));
+    }
+  }
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) bf[(int64_t)I * ld + J] = any ? 1 : 0;
 }
 
 // thresh[0] = max(eps_rank^2, 1e-14 * max_i G[i][i])  (the Gram-form stand-in for "sigma_j < eps_rank", optimize.jl:297-302)

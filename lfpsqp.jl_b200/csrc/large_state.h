@@ -51,6 +51,7 @@ struct LargeState {
   // zero-slab map of J for the Gram (large_gemm.cuh): J is stored dense, but the SYRK skips K chunks in which the rows of a tile
   // are all zero.  gram_mode 0: not decided (scan + skipping kernel, density read with the next control block), 1: block-sparse
   // (keep scanning: values may change), 2: dense (plain kernel, no scan; sticky -- zeros appearing later only cost time)
+  int *blkflag = nullptr;      // [nblk][nblk] block structure of G / L for the factorisation (large_gemm.cuh::GemmExt::bf)
   unsigned char *nzmap = nullptr;
   int64_t nz_ld = 0;
   int nz_rows = 0, gram_mode = 0, max_dyn_smem = 48 * 1024;
