@@ -404,6 +404,7 @@ static int factorize(lfpsqp_ctx *c, LargeState &S) {
   // return at once.  A dense G costs one 15 us scan; a block-sparse one (Thomson: G is diagonal) keeps only the potf2 chain.
   GemmExt F1, F2, F3;
   const GemmExt *f1 = nullptr, *f2 = nullptr;
+  int *done = nullptr;
   {
     const char *env = getenv("LFPSQP_GRAM_SKIP");
     if (S.blkflag && nblk > 1 && !(env && env[0] == '0')) {
@@ -412,6 +413,10 @@ static int factorize(lfpsqp_ctx *c, LargeState &S) {
       F1.bf = S.blkflag; F1.bf_ld = nblk; F1.bf_n = nblk; F1.bf_mode = 1;
       F2 = F1; F2.bf_mode = 2; F3 = F1; F3.bf_mode = 3;
       f1 = &F1; f2 = &F2;
+      done = S.blkflag + (size_t)nblk * nblk;
+      // diagonal blocks nothing will ever update: factorised now, in parallel; the chain below skips them
+      potf2_inv_indep_kernel<NB><<<nblk, 256, psm, S.stream>>>(S.G, ldm, m, S.Dblk, S.thresh, &S.ctrl->rankflag, S.blkflag, nblk, done);
+      S.launches++;
     }
   }
   // Right-looking blocked Cholesky with LOOK-AHEAD: the single-CTA factorisation of diagonal block b+1 (latency-bound, ~50 us)
@@ -423,7 +428,7 @@ static int factorize(lfpsqp_ctx *c, LargeState &S) {
     cudaEventCreateWithFlags(&S.ev_panel, cudaEventDisableTiming); cudaEventCreateWithFlags(&S.ev_potf, cudaEventDisableTiming);
   }
   cudaStream_t main_s = S.stream, side_s = S.side_stream ? S.side_stream : S.stream;
-  potf2_inv_kernel<NB><<<1, 256, psm, main_s>>>(S.G, ldm, std::min(NB, m), S.Dblk, S.thresh, &S.ctrl->rankflag);
+  potf2_inv_kernel<NB><<<1, 256, psm, main_s>>>(S.G, ldm, std::min(NB, m), S.Dblk, S.thresh, &S.ctrl->rankflag, done, 0);
   S.launches++;
   for (int b = 0; b < nblk; b++) {
     int j0 = b * NB, nb = std::min(NB, m - j0), rem = m - j0 - nb;
@@ -437,7 +442,7 @@ static int factorize(lfpsqp_ctx *c, LargeState &S) {
     F2.bf_a0 = b + 1; F2.bf_b0 = b + 1; F2.bf_col = b;
     gemm_nt(S, rem, nb2, nb, A21, ldm, A21, ldm, A22, ldm, GEMM_SUB, 0, f2);                     // panel of block b+1: A22[:, 0:nb2] -= L21 L21[0:nb2]'
     if (side_s != main_s) { cudaEventRecord(S.ev_panel, main_s); cudaStreamWaitEvent(side_s, S.ev_panel, 0); }
-    potf2_inv_kernel<NB><<<1, 256, psm, side_s>>>(A22, ldm, nb2, S.Dblk + (size_t)(b + 1) * NB * NB, S.thresh, &S.ctrl->rankflag);
+    potf2_inv_kernel<NB><<<1, 256, psm, side_s>>>(A22, ldm, nb2, S.Dblk + (size_t)(b + 1) * NB * NB, S.thresh, &S.ctrl->rankflag, done, b + 1);
     S.launches++;
     if (side_s != main_s) cudaEventRecord(S.ev_potf, side_s);
     if (rem2 > 0) {                                                                              // the rest of A22 -= L21 L21' (lower)
@@ -1140,7 +1145,7 @@ extern "C" int lfpsqp_large_setup(lfpsqp_ctx *c, int family, int64_t n_global, i
   ok &= dalloc(S, &S.Dblk, ((mm + 63) / 64) * 64 * 64); ok &= dalloc(S, &S.tmp64, mm * 64); ok &= dalloc(S, &S.thresh, 8);
   S.nz_rows = (int)((mm + 63) / 64); S.nz_ld = (int64_t)((S.ldj + GM_BK - 1) / GM_BK + 64) / 64 * 64; S.gram_mode = 0; S.nz_pending = false;
   ok &= dalloc(S, &S.nzmap, (size_t)S.nz_rows * S.nz_ld);
-  ok &= dalloc(S, &S.blkflag, (size_t)S.nz_rows * S.nz_rows + 1);
+  ok &= dalloc(S, &S.blkflag, (size_t)S.nz_rows * S.nz_rows + S.nz_rows + 1);   // + done[nblk]
   { int dev = 0, v = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev); if (v > 2048) S.max_dyn_smem = v - 1024; }
   S.gemm_ws_bytes = std::max<size_t>((size_t)16 * mm * 64 * 8, std::min<size_t>(mm * mm * 8 * 16, (size_t)1 << 30));
   { char *ws = nullptr; ok &= dalloc(S, &ws, S.gemm_ws_bytes); S.gemm_ws = (double *)ws; }
@@ -1190,6 +1195,7 @@ extern "C" int lfpsqp_large_setup(lfpsqp_ctx *c, int family, int64_t n_global, i
   { int dev = 0, v = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (v > 2048) CK(cudaFuncSetAttribute(dgemm_nt_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v - 1024)); }   // static shared memory counts too
   cudaFuncSetAttribute(potf2_inv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 64 * 65 * sizeof(double)));
+  cudaFuncSetAttribute(potf2_inv_indep_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 64 * 65 * sizeof(double)));
   // the staged m-vector of tri_gemv / the row-split of cols_dot exceed the 48 KB default for m > 6144
   CK(cudaFuncSetAttribute(tri_gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(mm * sizeof(double), 1024)));
   CK(cudaFuncSetAttribute(cols_dot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(mm * sizeof(double), 1024)));

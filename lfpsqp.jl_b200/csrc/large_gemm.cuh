@@ -271,8 +271,7 @@ __global__ void __launch_bounds__(256) zero_slab_map_kernel(const double *__rest
 // (row-major NB x NB, zeros above the diagonal and outside nb_act) to Dout.
 // flag[0] is set to 1 when a pivot is not > thresh (rank deficiency, cf. optimize.jl:297-302).
 template <int NB>
-__global__ void __launch_bounds__(256) potf2_inv_kernel(double *A, int64_t lda, int nb_act, double *Dout,
-                                                        const double *thresh_p, int *flag) {
+__device__ __forceinline__ void potf2_inv_body(double *A, int64_t lda, int nb_act, double *Dout, const double *thresh_p, int *flag) {
   static_assert(NB == 64, "register tiling assumes a 64 x 64 block");
   extern __shared__ double psm[];
   double (*Ls)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(psm);
@@ -360,6 +359,26 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double *A, int64_t lda, 
     if (r < nb_act && c < nb_act) A[(int64_t)r * lda + c] = Ls[r][c];
     Dout[e] = (r < nb_act && c < nb_act) ? Ds[r][c] : 0.0;
   }
+}
+// chain call of the blocked Cholesky; done[b] != 0: the block was already factorised by potf2_inv_indep_kernel
+template <int NB>
+__global__ void __launch_bounds__(256) potf2_inv_kernel(double *A, int64_t lda, int nb_act, double *Dout,
+                                                        const double *thresh_p, int *flag, const int *done = nullptr, int b = 0) {
+  if (done && done[b]) return;
+  potf2_inv_body<NB>(A, lda, nb_act, Dout, thresh_p, flag);
+}
+// Diagonal blocks with no structural non-zero to their left (bf row b, columns < b) never receive an update: they are
+// factorised here, all at once (one CTA per block), before the chain starts.  Thomson: G is diagonal -> all 64 blocks.
+template <int NB>
+__global__ void __launch_bounds__(256) potf2_inv_indep_kernel(double *G, int64_t ldg, int m, double *Dblk, const double *thresh_p,
+                                                              int *flag, const int *bf, int nblk, int *done) {
+  const int b = blockIdx.x;
+  int any = 0;
+  for (int J = threadIdx.x; J < b; J += 256) any |= bf[(int64_t)b * nblk + J];
+  any = __syncthreads_or(any);
+  if (any) { if (threadIdx.x == 0) done[b] = 0; return; }
+  potf2_inv_body<NB>(G + (int64_t)b * NB * ldg + (int64_t)b * NB, ldg, min(NB, m - b * NB), Dblk + (size_t)b * NB * NB, thresh_p, flag);
+  if (threadIdx.x == 0) done[b] = 1;
 }
 
 // bf[I * ld + J] = 1 iff the 64 x 64 block (I, J), I >= J, of the lower triangle of G holds a non-zero (or NaN); grid (nblk, nblk)
