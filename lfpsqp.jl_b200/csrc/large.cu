@@ -52,6 +52,7 @@ static int read_ctrl(lfpsqp_ctx *c, LargeState &S) {
   CK(cudaStreamSynchronize(S.stream));
   CK(cudaGetLastError());   // a refused launch (bad configuration) since the last check must not pass silently
   if (S.hctrl->commfail) return c->fail(LFPSQP_ERR_COMM, "a peer-memory exchange of the column-sharded mode timed out (a rank died or fell > 4 s behind)");
+  if (S.gdep_pending) { S.gdep_pending = false; S.g_blockdiag = (S.hctrl->g_dependent == 0) ? 1 : 0; }
   if (S.nz_pending) {       // density of the zero-slab map of J -> keep skipping (block-sparse J) or use the plain SYRK from now on
     S.nz_pending = false;
     const double total = (double)S.nz_rows * (double)std::max<int64_t>(S.nz_ld, 1);
@@ -405,6 +406,7 @@ static int factorize(lfpsqp_ctx *c, LargeState &S) {
   GemmExt F1, F2, F3;
   const GemmExt *f1 = nullptr, *f2 = nullptr;
   int *done = nullptr;
+  bool chain = true;
   {
     const char *env = getenv("LFPSQP_GRAM_SKIP");
     if (S.blkflag && nblk > 1 && !(env && env[0] == '0')) {
@@ -415,8 +417,15 @@ static int factorize(lfpsqp_ctx *c, LargeState &S) {
       f1 = &F1; f2 = &F2;
       done = S.blkflag + (size_t)nblk * nblk;
       // diagonal blocks nothing will ever update: factorised now, in parallel; the chain below skips them
-      potf2_inv_indep_kernel<NB><<<nblk, 256, psm, S.stream>>>(S.G, ldm, m, S.Dblk, S.thresh, &S.ctrl->rankflag, S.blkflag, nblk, done);
+      cudaMemsetAsync(&S.ctrl->g_dependent, 0, sizeof(int), S.stream);
+      potf2_inv_indep_kernel<NB><<<nblk, 256, psm, S.stream>>>(S.G, ldm, m, S.Dblk, S.thresh, &S.ctrl->rankflag, S.blkflag, nblk, done,
+                                                               &S.ctrl->g_dependent);
       S.launches++;
+      if (S.g_blockdiag == 1) {   // block diagonal last time: look now (one short sync instead of ~5 launches per block)
+        cudaMemcpyAsync(&S.hctrl->g_dependent, &S.ctrl->g_dependent, sizeof(int), cudaMemcpyDeviceToHost, S.stream);
+        if (cudaStreamSynchronize(S.stream) == cudaSuccess && S.hctrl->g_dependent == 0) chain = false;
+        else S.g_blockdiag = 0;
+      } else S.gdep_pending = true;
     }
   }
   // Right-looking blocked Cholesky with LOOK-AHEAD: the single-CTA factorisation of diagonal block b+1 (latency-bound, ~50 us)
@@ -428,9 +437,8 @@ static int factorize(lfpsqp_ctx *c, LargeState &S) {
     cudaEventCreateWithFlags(&S.ev_panel, cudaEventDisableTiming); cudaEventCreateWithFlags(&S.ev_potf, cudaEventDisableTiming);
   }
   cudaStream_t main_s = S.stream, side_s = S.side_stream ? S.side_stream : S.stream;
-  potf2_inv_kernel<NB><<<1, 256, psm, main_s>>>(S.G, ldm, std::min(NB, m), S.Dblk, S.thresh, &S.ctrl->rankflag, done, 0);
-  S.launches++;
-  for (int b = 0; b < nblk; b++) {
+  if (chain) { potf2_inv_kernel<NB><<<1, 256, psm, main_s>>>(S.G, ldm, std::min(NB, m), S.Dblk, S.thresh, &S.ctrl->rankflag, done, 0); S.launches++; }
+  for (int b = 0; chain && b < nblk; b++) {
     int j0 = b * NB, nb = std::min(NB, m - j0), rem = m - j0 - nb;
     double *Db = S.Dblk + (size_t)b * NB * NB;
     if (rem <= 0) break;
@@ -459,7 +467,7 @@ static int factorize(lfpsqp_ctx *c, LargeState &S) {
   cudaMemsetAsync(S.Linv, 0, (size_t)m * ldm * sizeof(double), S.stream);
   diag_blocks_kernel<<<nblk, 256, 0, S.stream>>>(S.Dblk, NB, m, S.XT, S.Linv, ldm);
   S.launches++;
-  for (int B = NB; B < m; B *= 2) {
+  for (int B = NB; chain && B < m; B *= 2) {   // (a block-diagonal L has a block-diagonal inverse: level 0 is all of it)
     const int nfull = m / (2 * B);                      // pairs with two complete blocks
     const int o_r = nfull * 2 * B, B2r = m - o_r - B;   // ragged last pair: L22 is B2r x B2r (if > 0)
     for (int part = 0; part < 2; part++) {
@@ -1143,7 +1151,7 @@ extern "C" int lfpsqp_large_setup(lfpsqp_ctx *c, int family, int64_t n_global, i
   ok &= dalloc(S, &S.J, mm * S.ldj);
   ok &= dalloc(S, &S.G, mm * S.ldm); ok &= dalloc(S, &S.XT, mm * S.ldm); ok &= dalloc(S, &S.Linv, mm * S.ldm);
   ok &= dalloc(S, &S.Dblk, ((mm + 63) / 64) * 64 * 64); ok &= dalloc(S, &S.tmp64, mm * 64); ok &= dalloc(S, &S.thresh, 8);
-  S.nz_rows = (int)((mm + 63) / 64); S.nz_ld = (int64_t)((S.ldj + GM_BK - 1) / GM_BK + 64) / 64 * 64; S.gram_mode = 0; S.nz_pending = false;
+  S.nz_rows = (int)((mm + 63) / 64); S.nz_ld = (int64_t)((S.ldj + GM_BK - 1) / GM_BK + 64) / 64 * 64; S.gram_mode = 0; S.nz_pending = false; S.g_blockdiag = 0; S.gdep_pending = false;
   ok &= dalloc(S, &S.nzmap, (size_t)S.nz_rows * S.nz_ld);
   ok &= dalloc(S, &S.blkflag, (size_t)S.nz_rows * S.nz_rows + S.nz_rows + 1);   // + done[nblk]
   { int dev = 0, v = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev); if (v > 2048) S.max_dyn_smem = v - 1024; }

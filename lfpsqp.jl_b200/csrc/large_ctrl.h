@@ -16,6 +16,7 @@ struct LargeCtrl {
   int rankflag, commfail;    // rankflag: Cholesky pivot below the rank threshold ; commfail: a peer-memory exchange timed out
   double ldiag_min, ldiag_max;   // explicit-inverse guard (large.cu::factorize): estimate of lambda_min(G), trace(G)
   unsigned long long nz_count;   // non-zero entries of the zero-slab map of J (large_gemm.cuh::zero_slab_map_kernel)
+  int g_dependent, pad_;         // diagonal blocks of G with a structural non-zero to their left (potf2_inv_indep_kernel); 0 = block diagonal
 };
 
 // Peer-memory region every rank exports over CUDA IPC (comm.cu).  First part: pull-model all-reduce kernels of comm.cu

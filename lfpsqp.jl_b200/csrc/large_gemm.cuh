@@ -371,12 +371,12 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double *A, int64_t lda, 
 // factorised here, all at once (one CTA per block), before the chain starts.  Thomson: G is diagonal -> all 64 blocks.
 template <int NB>
 __global__ void __launch_bounds__(256) potf2_inv_indep_kernel(double *G, int64_t ldg, int m, double *Dblk, const double *thresh_p,
-                                                              int *flag, const int *bf, int nblk, int *done) {
+                                                              int *flag, const int *bf, int nblk, int *done, int *dependent) {
   const int b = blockIdx.x;
   int any = 0;
   for (int J = threadIdx.x; J < b; J += 256) any |= bf[(int64_t)b * nblk + J];
   any = __syncthreads_or(any);
-  if (any) { if (threadIdx.x == 0) done[b] = 0; return; }
+  if (any) { if (threadIdx.x == 0) { done[b] = 0; atomicAdd(dependent, 1); } return; }
   potf2_inv_body<NB>(G + (int64_t)b * NB * ldg + (int64_t)b * NB, ldg, min(NB, m - b * NB), Dblk + (size_t)b * NB * NB, thresh_p, flag);
   if (threadIdx.x == 0) done[b] = 1;
 }

@@ -51,6 +51,11 @@ struct LargeState {
   // zero-slab map of J for the Gram (large_gemm.cuh): J is stored dense, but the SYRK skips K chunks in which the rows of a tile
   // are all zero.  gram_mode 0: not decided (scan + skipping kernel, density read with the next control block), 1: block-sparse
   // (keep scanning: values may change), 2: dense (plain kernel, no scan; sticky -- zeros appearing later only cost time)
+  // g_blockdiag: the previous factorisation found G block diagonal (every diagonal block independent) -> the next one reads the
+  // count back right after the parallel diagonal factorisation and, if it is still 0, enqueues neither the Cholesky chain nor the
+  // inverse's GEMM levels (hundreds of launches that would all return at once)
+  int g_blockdiag = 0;
+  bool gdep_pending = false;
   int *blkflag = nullptr;      // [nblk][nblk] block structure of G / L for the factorisation (large_gemm.cuh::GemmExt::bf)
   unsigned char *nzmap = nullptr;
   int64_t nz_ld = 0;
