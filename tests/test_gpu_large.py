@@ -456,3 +456,34 @@ def test_zero_slab_skipping_gram_is_bit_identical(L, monkeypatch):
     J = Qb * xq[None, :] + Ab
     assert rel(np.tril(fac["G"]), np.tril((Q * xq[None, :] + A) @ (Q * xq[None, :] + A).T)) < 1e-14
     assert J.shape == (m, n)
+
+
+def test_block_diagonal_gram_chain_skip_tracks_structure_changes(L, monkeypatch):
+    # A Gram that is block diagonal (64 x 64 blocks) needs no Cholesky chain: after one factorisation found that, the next ones
+    # verify it with a readback and skip the chain.  The structure may change with x: J = Q o x + A with one coupling entry
+    # Q[0, 1500] between the column supports of block 0 and block 1 -> coupled iff x[1500] != 0.  Every factorisation must equal
+    # the plain dense path bit for bit, whatever came before it.
+    n, m = 3072, 192
+    Q, A, b, xt, w, x0 = L.make_diagquad(n, m, seed=21, cond=20.0)
+    sup = np.zeros((m, n), dtype=bool)
+    for blk in range(3):
+        sup[64 * blk:64 * blk + 64, 1000 * blk:1000 * blk + 1000] = True
+    A = np.where(sup, A, 0.0); Q = np.where(sup, Q, 0.0)
+    Q[0, 1500] = 0.7
+    xa = x0.copy(); xa[1500] = 0.0          # block diagonal
+    xb = x0.copy(); xb[1500] = 1.3          # block (1, 0) of G becomes non-zero
+    fam = lambda: L.families.diagquad(Q, A, b, xt, w)
+    monkeypatch.setenv("LFPSQP_GRAM_SKIP", "0")
+    Pref = L.LargeProblem(fam())
+    ref = {"a": Pref.factor(xa), "b": Pref.factor(xb)}
+    monkeypatch.delenv("LFPSQP_GRAM_SKIP")
+    assert np.all(np.tril(ref["a"]["G"], -1)[64:, :64] == 0.0) and np.any(ref["b"]["G"][64:128, :64] != 0.0)
+    P = L.LargeProblem(fam())
+    for step, which in enumerate("aaabbaab"):
+        fac = P.factor(xa if which == "a" else xb)
+        for key in ("G", "L", "Linv"):
+            assert np.array_equal(np.tril(fac[key]), np.tril(ref[which][key])), (step, which, key)
+    v = np.random.default_rng(2).standard_normal(n)
+    pv, lam = P.project(v)
+    J = Q * xb[None, :] + A
+    assert np.linalg.norm(J @ pv) < 1e-11 * np.linalg.norm(v)
