@@ -72,3 +72,19 @@ if mode in ("all", "r2"):
     P = L.LargeProblem(L.families.diagquad(Q, A, b, xt, w)); P.factor(x0, want=())
     print(P.projcg(x0, lam=np.zeros(12), tol=1e-8, maxit=20)["iters"])
     del os.environ["LFPSQP_EXPLICIT_INVERSE"]
+if mode in ("all", "r2f"):
+    # factorisation with structure detection: zero-slab Gram (SKIP kernel), block flags, parallel diagonal blocks, chain skip after
+    # the read-back, batched / triangle-bounded GEMMs of the recursive inverse with ragged and odd sizes, odd-N split-K workspace
+    x0 = rng.standard_normal((150, 3)); x0 /= np.linalg.norm(x0, axis=1, keepdims=True); x0 = x0.ravel()
+    P = L.LargeProblem(L.families.thomson(150))
+    for rep in range(3): fac = P.factor(x0)
+    print("thomson-150 factor x3:", fac["rank_deficient"], P.solve(x0, L.LFPSQPParams(maxiter=2))[3])
+    for (n, m) in [(1200, 193), (1100, 65), (900, 130)]:
+        Q, A, b, xt, w, xq = L.make_diagquad(n, m, seed=n + m, cond=50.0)
+        band = np.zeros((m, n), dtype=bool)
+        for i in range(m):
+            lo = (i * 7) % (n - 200); band[i, lo:lo + 150] = True
+        for QQ, AA in ((Q, A), (np.where(band, Q, 0.0), np.where(band, A, 0.0))):
+            P = L.LargeProblem(L.families.diagquad(QQ, AA, b, xt, w))
+            for rep in range(2): fac = P.factor(xq)
+            print(n, m, "factor ok", fac["rank_deficient"])
