@@ -139,6 +139,13 @@ static void gemm_nt(LargeState &S, int M, int N, int K, const double *A, int64_t
 
 static void rows_dot(LargeState &S, const double *Jm, int64_t ld, int m, int64_t ncols, const double *v, double *t, int pred) {
   if (m <= 0) return;
+  if (Jm == S.J && S.jmap_valid && S.gram_mode == 1) {   // block-sparse J: same pass, loads of all-zero slabs not issued
+    if (m >= 8 * S.sm_count) rows_dot_kernel<4, true><<<(m + 3) / 4, 256, 0, S.stream>>>(Jm, ld, m, ncols, v, t, S.ctrl, pred, S.nzmap, S.nz_ld);
+    else if (m >= 2 * S.sm_count) rows_dot_kernel<2, true><<<(m + 1) / 2, 256, 0, S.stream>>>(Jm, ld, m, ncols, v, t, S.ctrl, pred, S.nzmap, S.nz_ld);
+    else rows_dot_kernel<1, true><<<m, 256, 0, S.stream>>>(Jm, ld, m, ncols, v, t, S.ctrl, pred, S.nzmap, S.nz_ld);
+    S.launches++;
+    return;
+  }
   if (m >= 8 * S.sm_count) rows_dot_kernel<4><<<(m + 3) / 4, 256, 0, S.stream>>>(Jm, ld, m, ncols, v, t, S.ctrl, pred);
   else if (m >= 2 * S.sm_count) rows_dot_kernel<2><<<(m + 1) / 2, 256, 0, S.stream>>>(Jm, ld, m, ncols, v, t, S.ctrl, pred);
   else rows_dot_kernel<1><<<m, 256, 0, S.stream>>>(Jm, ld, m, ncols, v, t, S.ctrl, pred);
@@ -147,7 +154,10 @@ static void rows_dot(LargeState &S, const double *Jm, int64_t ld, int m, int64_t
 static void cols_dot(LargeState &S, const double *Jm, int64_t ld, int m, int64_t ncols, const double *u, int pred) {
   if (m <= 0) return;
   dim3 grid((unsigned)((ncols + 511) / 512), S.nsplit);
-  cols_dot_kernel<<<grid, 256, S.rows_per_split * sizeof(double), S.stream>>>(Jm, ld, m, ncols, u, S.cpart, S.rows_per_split, S.ctrl, pred);
+  if (Jm == S.J && S.jmap_valid && S.gram_mode == 1)
+    cols_dot_kernel<true><<<grid, 256, S.rows_per_split * sizeof(double), S.stream>>>(Jm, ld, m, ncols, u, S.cpart, S.rows_per_split, S.ctrl, pred, S.nzmap, S.nz_ld);
+  else
+    cols_dot_kernel<false><<<grid, 256, S.rows_per_split * sizeof(double), S.stream>>>(Jm, ld, m, ncols, u, S.cpart, S.rows_per_split, S.ctrl, pred);
   S.launches++;
 }
 // u = (J J')^-1 t through the cached factor: y = L^-1 t ; u = L^-T y
@@ -227,6 +237,7 @@ static void fam_grad(LargeState &S, double *g, const double *x) {
 }
 // cval = c(x); with Jout also the Jacobian (jac! writes both, autodiff_generators.jl:40-42)
 static void fam_c_jac(LargeState &S, double *Jout, double *cval, const double *x) {
+  if (Jout == S.J) S.jmap_valid = false;   // J is rewritten: its zero-slab map is stale until the next Gram scans it
   const int m = S.m;
   if (S.family == LFPSQP_FAM_HOST) {
     host_x(S, x);
@@ -349,7 +360,8 @@ static void gram_syrk(LargeState &S, const double *Jg) {
     S.launches++;
     X.nz = S.nzmap; X.nz_ld = S.nz_ld; X.nz_rows = S.nz_rows; ext = &X;
     if (S.gram_mode == 0) S.nz_pending = true;
-  }
+    S.jmap_valid = (Jg == S.J);   // with bounds the map describes J diag(Dy), whose zeros are not J's
+  } else S.jmap_valid = false;
   gemm_nt(S, m, m, (int)S.n_loc, Jg, S.ldj, Jg, S.ldj, S.G, S.ldm, GEMM_ASSIGN, 1, ext);
 }
 static void gram_only(LargeState &S) {   // S.G (lower tiles) = J W J', all-reduced
@@ -810,7 +822,7 @@ static int retract_nr(lfpsqp_ctx *c, LargeState &S, int *flag_out, int *it1) {
     // Good Broyden (:156-160): t2 = D' delta ; t1 = delta - D dc ; D += t1 t2' / (t2.dc)
     {
       dim3 grid((unsigned)((m + 511) / 512), S.nsplit);
-      cols_dot_kernel<<<grid, 256, S.rows_per_split * sizeof(double), S.stream>>>(D, ldm, m, m, t1, S.cpart, S.rows_per_split, S.ctrl, 0);
+      cols_dot_kernel<false><<<grid, 256, S.rows_per_split * sizeof(double), S.stream>>>(D, ldm, m, m, t1, S.cpart, S.rows_per_split, S.ctrl, 0);
       const double *cp = S.cpart; int ns = S.nsplit;
       vec(S, m, [=] __device__(int64_t a, double *acc) {
         double s = 0.0; for (int k = 0; k < ns; k++) s += cp[(int64_t)k * m + a];
@@ -1206,7 +1218,8 @@ extern "C" int lfpsqp_large_setup(lfpsqp_ctx *c, int family, int64_t n_global, i
   cudaFuncSetAttribute(potf2_inv_indep_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 64 * 65 * sizeof(double)));
   // the staged m-vector of tri_gemv / the row-split of cols_dot exceed the 48 KB default for m > 6144
   CK(cudaFuncSetAttribute(tri_gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(mm * sizeof(double), 1024)));
-  CK(cudaFuncSetAttribute(cols_dot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(mm * sizeof(double), 1024)));
+  CK(cudaFuncSetAttribute(cols_dot_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(mm * sizeof(double), 1024)));
+  CK(cudaFuncSetAttribute(cols_dot_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(mm * sizeof(double), 1024)));
   CK(cudaStreamSynchronize(S.stream));
   {
     const char *env = getenv("LFPSQP_FUSED_PROJCG");   // "0" selects the multi-kernel projcg loop (A/B measurements, tests)

@@ -22,10 +22,13 @@ namespace lfpsqp {
 
 // ------------------------------------------------------------------ pass 1: t[i] = sum_j J[i][j] v[j]
 // One CTA owns R full rows (no cross-CTA reduction). v is re-read from L2 once per R rows.
-template <int R>
+// SKIP: nz is the zero-slab map of J (large_gemm.cuh::zero_slab_map_kernel: 64 rows x 16 columns); loads of all-zero slabs are
+// not issued.  Same threads, same accumulation order, only "+ 0 * v" terms less: bit-identical to the dense pass.
+template <int R, bool SKIP = false>
 __global__ void __launch_bounds__(256) rows_dot_kernel(const double *__restrict__ J, int64_t ld, int m, int64_t ncols,
                                                        const double *__restrict__ v, double *__restrict__ t,
-                                                       const LargeCtrl *ctrl, int pred) {
+                                                       const LargeCtrl *ctrl, int pred, const unsigned char *__restrict__ nz = nullptr,
+                                                       int64_t nz_ld = 0) {
   if (pred == 1 && ctrl->status != 0) return;
   if (pred == 2 && ctrl->pcg_status != 0) return;
   __shared__ double sh[33];
@@ -46,11 +49,12 @@ __global__ void __launch_bounds__(256) rows_dot_kernel(const double *__restrict_
     for (int r = 0; r < R; r++) {
       if (row0 + r < m) {
         const double *row = J + (int64_t)(row0 + r) * ld;
+        const unsigned char *nzr = SKIP ? nz + (int64_t)((row0 + r) >> 6) * nz_ld : nullptr;
         double2 a[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           int64_t jj = j + (int64_t)u * 256;
-          a[u] = (jj < n2) ? ld_stream2(row + 2 * jj) : make_double2(0.0, 0.0);
+          a[u] = (jj < n2 && (!SKIP || nzr[jj >> 3])) ? ld_stream2(row + 2 * jj) : make_double2(0.0, 0.0);
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) acc[r] += a[u].x * vv[u].x + a[u].y * vv[u].y;
@@ -70,9 +74,11 @@ __global__ void __launch_bounds__(256) rows_dot_kernel(const double *__restrict_
 
 // ------------------------------------------------------------------ pass 2: cpart[rs][j] = sum_{i in split rs} J[i][j] u[i]
 // CTA = 512 columns (2 per thread) x one row split; u chunk staged in shared memory.
+template <bool SKIP = false>
 __global__ void __launch_bounds__(256) cols_dot_kernel(const double *__restrict__ J, int64_t ld, int m, int64_t ncols,
                                                        const double *__restrict__ u, double *__restrict__ cpart,
-                                                       int rows_per_split, const LargeCtrl *ctrl, int pred) {
+                                                       int rows_per_split, const LargeCtrl *ctrl, int pred,
+                                                       const unsigned char *__restrict__ nz = nullptr, int64_t nz_ld = 0) {
   if (pred == 1 && ctrl->status != 0) return;
   if (pred == 2 && ctrl->pcg_status != 0) return;
   extern __shared__ double us[];
@@ -87,15 +93,20 @@ __global__ void __launch_bounds__(256) cols_dot_kernel(const double *__restrict_
   const double *base = J + (int64_t)i0 * ld + c;
   int i = 0;
   const int nr = i1 - i0;
+  const unsigned char *nzc = SKIP ? nz + (c >> 4) : nullptr;   // this thread's K chunk; one map row per 64 rows of J
   if (pair) {
     for (; i + 8 <= nr; i += 8) {
+      if (SKIP && !(nzc[(int64_t)((i0 + i) >> 6) * nz_ld] | nzc[(int64_t)((i0 + i + 7) >> 6) * nz_ld])) continue;   // 8 zero rows: a += 0 * w
       double2 q[8];
 #pragma unroll
       for (int k = 0; k < 8; k++) q[k] = ld_stream2(base + (int64_t)(i + k) * ld);
 #pragma unroll
       for (int k = 0; k < 8; k++) { double w = us[i + k]; a0 += q[k].x * w; a1 += q[k].y * w; }
     }
-    for (; i < nr; i++) { double2 q = ld_stream2(base + (int64_t)i * ld); double w = us[i]; a0 += q.x * w; a1 += q.y * w; }
+    for (; i < nr; i++) {
+      if (SKIP && !nzc[(int64_t)((i0 + i) >> 6) * nz_ld]) continue;
+      double2 q = ld_stream2(base + (int64_t)i * ld); double w = us[i]; a0 += q.x * w; a1 += q.y * w;
+    }
     *reinterpret_cast<double2 *>(cpart + (int64_t)rs * ncols + c) = make_double2(a0, a1);
   } else {
     for (; i < nr; i++) a0 += base[(int64_t)i * ld] * us[i];

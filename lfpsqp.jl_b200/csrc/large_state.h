@@ -61,6 +61,8 @@ struct LargeState {
   int64_t nz_ld = 0;
   int nz_rows = 0, gram_mode = 0, max_dyn_smem = 48 * 1024;
   bool nz_pending = false;
+  bool jmap_valid = false;   // nzmap describes the CURRENT contents of S.J (scanned by the last Gram, J not rewritten since): the
+                             // unfused passes over J (rows_dot / cols_dot) skip its all-zero slabs too
   // n_loc vectors
   double *x = nullptr, *xnew = nullptr, *xtil = nullptr, *g = nullptr, *d = nullptr, *nd = nullptr, *w0 = nullptr,
          *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr, *hdiag = nullptr, *ex[4] = {nullptr, nullptr, nullptr, nullptr};

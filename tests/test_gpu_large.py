@@ -456,6 +456,18 @@ def test_zero_slab_skipping_gram_is_bit_identical(L, monkeypatch):
     J = Qb * xq[None, :] + Ab
     assert rel(np.tril(fac["G"]), np.tril((Q * xq[None, :] + A) @ (Q * xq[None, :] + A).T)) < 1e-14
     assert J.shape == (m, n)
+    # whole solves: the unfused passes over J (projection, projcg) skip the all-zero slabs as well -- same iterates, bit for bit
+    bq = 0.5 * Qb @ (xq * xq) + Ab @ xq
+    solves = [("thomson", lambda: L.LargeProblem(L.families.thomson(npts)), x0),
+              ("banded diagquad", lambda: L.LargeProblem(L.families.diagquad(Qb, Ab, bq, xt, w)), xq)]
+    for name, make, xs in solves:
+        for prm in (L.LFPSQPParams(maxiter=12), L.LFPSQPParams(maxiter=12, do_project_retract=False)):
+            monkeypatch.setenv("LFPSQP_GRAM_SKIP", "0")
+            xr, objr, lamr, infor = make().solve(xs, prm)
+            monkeypatch.delenv("LFPSQP_GRAM_SKIP")
+            xg, objg, lamg, infog = make().solve(xs, prm)
+            assert infor.iter == infog.iter and infor.condition == infog.condition, name
+            assert np.array_equal(xr, xg) and np.array_equal(np.asarray(objr), np.asarray(objg)) and np.array_equal(lamr, lamg), name
 
 
 def test_block_diagonal_gram_chain_skip_tracks_structure_changes(L, monkeypatch):
