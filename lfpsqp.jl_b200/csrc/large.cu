@@ -110,9 +110,11 @@ static void gemm_nt(LargeState &S, int M, int N, int K, const double *A, int64_t
   const int kchunks = (K + GM_BK - 1) / GM_BK, per = (kchunks + ksplit - 1) / ksplit;
   const size_t skip_smem = dgemm_smem_bytes<128>() + (size_t)per * sizeof(int);
   const bool skip = X.nz && !narrow && skip_smem <= (size_t)S.max_dyn_smem;
+  const bool lean = !ext;   // plain product: the instantiation without the extras' prologue
   if (ksplit == 1) {
     if (skip) dgemm_nt_kernel<128, true><<<grid, 256, skip_smem, S.stream>>>(M, N, K, A, lda, B, ldb, C, ldc, mode, lower, 1, 0, X);
     else if (narrow) dgemm_nt_kernel<64><<<grid, 256, dgemm_smem_bytes<64>(), S.stream>>>(M, N, K, A, lda, B, ldb, C, ldc, mode, lower, 1, 0, X);
+    else if (lean) dgemm_nt_kernel<128, false, false><<<grid, 256, dgemm_smem_bytes<128>(), S.stream>>>(M, N, K, A, lda, B, ldb, C, ldc, mode, lower, 1, 0, X);
     else dgemm_nt_kernel<128><<<grid, 256, dgemm_smem_bytes<128>(), S.stream>>>(M, N, K, A, lda, B, ldb, C, ldc, mode, lower, 1, 0, X);
     S.launches++;
   } else {
@@ -121,6 +123,7 @@ static void gemm_nt(LargeState &S, int M, int N, int K, const double *A, int64_t
     const int64_t stride = (int64_t)M * ldw;
     if (skip) dgemm_nt_kernel<128, true><<<grid, 256, skip_smem, S.stream>>>(M, N, K, A, lda, B, ldb, S.gemm_ws, ldw, GEMM_ASSIGN, lower, ksplit, stride, X);
     else if (narrow) dgemm_nt_kernel<64><<<grid, 256, dgemm_smem_bytes<64>(), S.stream>>>(M, N, K, A, lda, B, ldb, S.gemm_ws, ldw, GEMM_ASSIGN, lower, ksplit, stride, X);
+    else if (lean) dgemm_nt_kernel<128, false, false><<<grid, 256, dgemm_smem_bytes<128>(), S.stream>>>(M, N, K, A, lda, B, ldb, S.gemm_ws, ldw, GEMM_ASSIGN, lower, ksplit, stride, X);
     else dgemm_nt_kernel<128><<<grid, 256, dgemm_smem_bytes<128>(), S.stream>>>(M, N, K, A, lda, B, ldb, S.gemm_ws, ldw, GEMM_ASSIGN, lower, ksplit, stride, X);
     const double *ws = S.gemm_ws;
     const double sgn = (mode == GEMM_ASSIGN_NEG) ? -1.0 : 1.0;
@@ -1211,6 +1214,7 @@ extern "C" int lfpsqp_large_setup(lfpsqp_ctx *c, int family, int64_t n_global, i
     if ((((uintptr_t)S.p_A) & 15) || (((uintptr_t)S.p_Q) & 15)) { lfpsqp_large_release(c); return c->fail(LFPSQP_ERR_ARG, "parameter blob must be 16-byte aligned"); }
   }
   cudaFuncSetAttribute(dgemm_nt_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgemm_smem_bytes<128>());
+  cudaFuncSetAttribute(dgemm_nt_kernel<128, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgemm_smem_bytes<128>());
   cudaFuncSetAttribute(dgemm_nt_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgemm_smem_bytes<64>());
   { int dev = 0, v = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (v > 2048) CK(cudaFuncSetAttribute(dgemm_nt_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v - 1024)); }   // static shared memory counts too

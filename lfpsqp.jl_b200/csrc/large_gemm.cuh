@@ -63,7 +63,9 @@ struct GemmExt {
 // lower_only: skip tiles strictly above the diagonal (SYRK / symmetric trailing update); tile (bi,bj) kept iff bi*BM+BM > bj*BN.
 // ksplit > 1: split-K, slice z writes its partial into C + z*c_split_stride (ASSIGN only); the caller reduces.
 // Requirements: lda, ldb even; A, B 16-byte aligned; K arbitrary (zero-filled), M, N arbitrary (predicated).
-template <int BN, bool SKIP = false>
+// EXT = false: the lean instantiation of the plain product (no batch / triangle bounds / block flags: X is ignored) -- the C5
+// Gram runs 2 % faster without the extra prologue and its registers (166 vs 178).
+template <int BN, bool SKIP = false, bool EXT = true>
 __global__ void __launch_bounds__(256) dgemm_nt_kernel(int M, int N, int K, const double *__restrict__ A, int64_t lda,
                                                        const double *__restrict__ B, int64_t ldb, double *__restrict__ C,
                                                        int64_t ldc, int mode, int lower_only, int ksplit,
@@ -77,13 +79,13 @@ __global__ void __launch_bounds__(256) dgemm_nt_kernel(int M, int N, int K, cons
   // tri bit 1: the K loop grows with the tile column -> walk the grid column by column from the last one, so that CTAs are issued
   // longest tile first (as the row-major order already does for tri bit 0); a mixed order left a long tile for the last wave
   int bi = blockIdx.y, bj = blockIdx.x;
-  if (X.tri & 2) {
+  if (EXT && (X.tri & 2)) {
     const int t = blockIdx.y * gridDim.x + blockIdx.x;
     bj = (int)gridDim.x - 1 - t / (int)gridDim.y; bi = t % (int)gridDim.y;
   }
   if (lower_only && (bi * BM + BM <= bj * BN)) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (X.bf_mode) {
+  if (EXT && X.bf_mode) {
     if (X.bf_mode == 3) {
       const int off = (int)blockIdx.z * X.bf_batch, w = X.bf_c1 - X.bf_c0, cnt = (X.bf_r1 - X.bf_r0) * w;
       int any = 0;
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(256) dgemm_nt_kernel(int M, int N, int K, cons
   const int wm = warp >> 2, wn = warp & 3;   // 2 x 4
   const int row0 = bi * BM, col0 = bj * BN;
   int zsplit = blockIdx.z;
-  if (X.batch > 1) {
+  if (EXT && X.batch > 1) {
     A += (int64_t)blockIdx.z * X.batch_a; B += (int64_t)blockIdx.z * X.batch_b; C += (int64_t)blockIdx.z * X.batch_c;
     zsplit = 0;
   }
@@ -117,8 +119,8 @@ __global__ void __launch_bounds__(256) dgemm_nt_kernel(int M, int N, int K, cons
   int kchunks = (K + BK - 1) / BK;
   int per = (kchunks + ksplit - 1) / ksplit;
   int kc0 = zsplit * per, kc1 = min(kchunks, kc0 + per);
-  if (X.tri & 1) kc0 = max(kc0, row0 / BK);
-  if (X.tri & 2) kc1 = min(kc1, (col0 + BN + BK - 1) / BK);
+  if (EXT && (X.tri & 1)) kc0 = max(kc0, row0 / BK);
+  if (EXT && (X.tri & 2)) kc1 = min(kc1, (col0 + BN + BK - 1) / BK);
   if (kc0 >= kc1) { kc1 = kc0; }
   // SKIP: ordered list of the K chunks of [kc0, kc1) in which both the A rows and the B rows of this tile have non-zeros
   int *klist = reinterpret_cast<int *>(gsm + (size_t)ST * (BM + BN) * LD);
