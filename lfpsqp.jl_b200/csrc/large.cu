@@ -172,8 +172,8 @@ static void gram_solve(LargeState &S, const double *t, double *u, double *u_copy
     S.launches++;
     return;
   }
-  tri_gemv_kernel<<<(m + 7) / 8, 256, m * sizeof(double), S.stream>>>(S.Linv, S.ldm, m, t, S.ty, 0, nullptr, S.ctrl, pred);
-  tri_gemv_kernel<<<(m + 7) / 8, 256, m * sizeof(double), S.stream>>>(S.XT, S.ldm, m, S.ty, u, 1, u_copy, S.ctrl, pred);
+  tri_gemv_kernel<<<(m + 7) / 8, 256, m * sizeof(double), S.stream>>>(S.Linv, S.ldm, m, t, S.ty, 0, nullptr, S.ctrl, pred, S.invflag_valid ? S.invflag : nullptr, S.nz_rows);
+  tri_gemv_kernel<<<(m + 7) / 8, 256, m * sizeof(double), S.stream>>>(S.XT, S.ldm, m, S.ty, u, 1, u_copy, S.ctrl, pred, S.invflag_valid ? S.invflag : nullptr, S.nz_rows);
   S.launches += 2;
 }
 
@@ -400,6 +400,7 @@ static int factorize_pinv(lfpsqp_ctx *c, LargeState &S, bool regram) {
 static int factorize(lfpsqp_ctx *c, LargeState &S) {
   const int m = S.m; const int64_t ldm = S.ldm;
   const double *Jg = S.J;
+  S.invflag_valid = false;
   if (S.ineq) {
     dim3 sg((unsigned)std::min<int64_t>(std::max<int64_t>(((S.n_loc >> 1) + 255) / 256, 1), 32), (unsigned)std::min(m, 65535));
     ineq_scale_cols_kernel<<<sg, 256, 0, S.stream>>>(S.J, S.ldj, m, S.n_loc, S.I.Dy, S.Jw);
@@ -504,6 +505,13 @@ static int factorize(lfpsqp_ctx *c, LargeState &S) {
       S.launches++;
     }
   }
+  // block structure of L^-1 for the unfused triangular passes (only worth it when G had structure: block-sparse J)
+  S.invflag_valid = false;
+  if (f1 && S.invflag && nblk <= 64 && S.gram_mode == 1) {
+    block_nz_kernel<<<dim3(nblk, nblk), 256, 0, S.stream>>>(S.Linv, ldm, m, S.invflag, nblk);
+    S.launches++;
+    S.invflag_valid = true;
+  }
   if (S.fused_ok && S.Ginv) {   // G^-1 = L^-T L^-1 = XT XT' for the fused projcg kernel (large_fused.cu): one more DMMA GEMM, m^3 flops
     gemm_nt(S, m, m, m, S.XT, ldm, S.XT, ldm, S.Ginv, ldm, GEMM_ASSIGN, 0);
     // guard of that shortcut: kappa = trace(G) * lambda_max(G^-1) >= cond(G) (8 power iterations on G^-1, ~0.1 ms); read_ctrl
@@ -578,7 +586,7 @@ static int projcg(lfpsqp_ctx *c, LargeState &S, double tol, int64_t maxit, int c
   if (S.family == LFPSQP_FAM_HOST) chunk = 1;   // the Hessian callback runs on the host: one status check per iteration
   if (cvec && S.m > 0 && !S.ineq) {
     const int m = S.m;
-    tri_gemv_kernel<<<(m + 7) / 8, 256, m * sizeof(double), S.stream>>>(S.XT, S.ldm, m, cvec, S.tu, 1, nullptr, S.ctrl, 0);   // L^-T c
+    tri_gemv_kernel<<<(m + 7) / 8, 256, m * sizeof(double), S.stream>>>(S.XT, S.ldm, m, cvec, S.tu, 1, nullptr, S.ctrl, 0, S.invflag_valid ? S.invflag : nullptr, S.nz_rows);   // L^-T c
     cols_dot(S, S.J, S.ldj, m, S.n_loc, S.tu, 0);
     const double *cp = S.cpart; const int64_t nl = S.n_loc;
     vec(S, n, [=] __device__(int64_t j, double *) { double s = 0.0; for (int k = 0; k < ns; k++) s += cp[(int64_t)k * nl + j]; xs[j] = s; });
@@ -644,7 +652,7 @@ static int projcg(lfpsqp_ctx *c, LargeState &S, double tol, int64_t maxit, int c
       vec(S, n, [=] __device__(int64_t i, double *) { Ad[i] = b[i] - Ad[i]; });
       rows_dot(S, S.J, S.ldj, S.m, S.n_loc, Ad, S.tm, 0);
       if (S.world > 1) comm_allreduce(S, S.tm, S.m);
-      tri_gemv_kernel<<<(S.m + 7) / 8, 256, S.m * sizeof(double), S.stream>>>(S.Linv, S.ldm, S.m, S.tm, lam_out, 0, nullptr, S.ctrl, 0);
+      tri_gemv_kernel<<<(S.m + 7) / 8, 256, S.m * sizeof(double), S.stream>>>(S.Linv, S.ldm, S.m, S.tm, lam_out, 0, nullptr, S.ctrl, 0, S.invflag_valid ? S.invflag : nullptr, S.nz_rows);
       S.launches += 2;
       (void)st_keep;
     }
@@ -808,7 +816,7 @@ static int retract_nr(lfpsqp_ctx *c, LargeState &S, int *flag_out, int *it1) {
     rows_dot(S, D, ldm, m, m, cval, t1, 0);                                              // D c
     vec(S, m, [=] __device__(int64_t a, double *) { t1[a] = -t1[a]; });                   // :140 delta = -D c
     // xnew += Q delta, Q = J' L^-T (:141)
-    tri_gemv_kernel<<<(m + 7) / 8, 256, m * sizeof(double), S.stream>>>(S.XT, ldm, m, t1, S.tu, 1, nullptr, S.ctrl, 0);
+    tri_gemv_kernel<<<(m + 7) / 8, 256, m * sizeof(double), S.stream>>>(S.XT, ldm, m, t1, S.tu, 1, nullptr, S.ctrl, 0, S.invflag_valid ? S.invflag : nullptr, S.nz_rows);
     cols_dot(S, S.J, S.ldj, m, n, S.tu, 0);
     { const double *cp = S.cpart; int ns = S.nsplit;
       // with bounds the basis is Q = PJct L^-T: x += Dy^2 w, y -= Dx Dy w, then y_retract! (:141-143)
@@ -1169,6 +1177,7 @@ extern "C" int lfpsqp_large_setup(lfpsqp_ctx *c, int family, int64_t n_global, i
   S.nz_rows = (int)((mm + 63) / 64); S.nz_ld = (int64_t)((S.ldj + GM_BK - 1) / GM_BK + 64) / 64 * 64; S.gram_mode = 0; S.nz_pending = false; S.g_blockdiag = 0; S.gdep_pending = false;
   ok &= dalloc(S, &S.nzmap, (size_t)S.nz_rows * S.nz_ld);
   ok &= dalloc(S, &S.blkflag, (size_t)S.nz_rows * S.nz_rows + S.nz_rows + 1);   // + done[nblk]
+  ok &= dalloc(S, &S.invflag, (size_t)S.nz_rows * S.nz_rows + 1);
   { int dev = 0, v = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev); if (v > 2048) S.max_dyn_smem = v - 1024; }
   S.gemm_ws_bytes = std::max<size_t>((size_t)16 * mm * 64 * 8, std::min<size_t>(mm * mm * 8 * 16, (size_t)1 << 30));
   { char *ws = nullptr; ok &= dalloc(S, &ws, S.gemm_ws_bytes); S.gemm_ws = (double *)ws; }

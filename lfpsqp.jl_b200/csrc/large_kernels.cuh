@@ -116,9 +116,12 @@ __global__ void __launch_bounds__(256) cols_dot_kernel(const double *__restrict_
 
 // ------------------------------------------------------------------ triangular GEMVs: out[i] = sum_k T[i][k] in[k]
 // lower: k <= i ; upper: k >= i.  One warp per row; `in` staged in shared memory.
+// bf (optional, nblk <= 64): block structure of L^-1 (large_gemm.cuh::block_nz_kernel on Linv; XT = Linv' uses the transposed
+// entry): terms of structurally zero 64 x 64 blocks are not loaded -- same lanes, same order, only "+ 0 * in[k]" terms less.
 __global__ void __launch_bounds__(256) tri_gemv_kernel(const double *__restrict__ T, int64_t ld, int m,
                                                        const double *__restrict__ in, double *__restrict__ out, int upper,
-                                                       double *__restrict__ out2, const LargeCtrl *ctrl, int pred) {
+                                                       double *__restrict__ out2, const LargeCtrl *ctrl, int pred,
+                                                       const int *__restrict__ bf = nullptr, int nblk = 0) {
   if (pred == 1 && ctrl->status != 0) return;
   if (pred == 2 && ctrl->pcg_status != 0) return;
   extern __shared__ double ins[];
@@ -129,6 +132,17 @@ __global__ void __launch_bounds__(256) tri_gemv_kernel(const double *__restrict_
   const int k0 = upper ? row : 0, k1 = upper ? m : row + 1;
   const double *tr = T + (int64_t)row * ld;
   double s = 0.0;
+  if (bf) {
+    const int ib = row >> 6;
+    unsigned long long mask = 0ULL;   // bit jb: block (ib, jb) of this triangle may be non-zero
+    {
+      const int j0 = lane, j1 = lane + 32;
+      const int f0 = (j0 < nblk) ? (upper ? bf[(int64_t)j0 * nblk + ib] : bf[(int64_t)ib * nblk + j0]) : 0;
+      const int f1 = (j1 < nblk) ? (upper ? bf[(int64_t)j1 * nblk + ib] : bf[(int64_t)ib * nblk + j1]) : 0;
+      mask = (unsigned long long)__ballot_sync(0xffffffffu, f0 != 0) | ((unsigned long long)__ballot_sync(0xffffffffu, f1 != 0) << 32);
+    }
+    for (int k = k0 + lane; k < k1; k += 32) if ((mask >> (k >> 6)) & 1ULL) s += tr[k] * ins[k];
+  } else
   for (int k = k0 + lane; k < k1; k += 32) s += tr[k] * ins[k];
   s = warp_sum(s);
   if (lane == 0) { out[row] = s; if (out2) out2[row] = s; }

@@ -56,6 +56,8 @@ struct LargeState {
   // inverse's GEMM levels (hundreds of launches that would all return at once)
   int g_blockdiag = 0;
   bool gdep_pending = false;
+  int *invflag = nullptr;      // [nblk][nblk] block structure of L^-1 (scanned after the inverse) for the triangular passes; null: off
+  bool invflag_valid = false;
   int *blkflag = nullptr;      // [nblk][nblk] block structure of G / L for the factorisation (large_gemm.cuh::GemmExt::bf)
   unsigned char *nzmap = nullptr;
   int64_t nz_ld = 0;
