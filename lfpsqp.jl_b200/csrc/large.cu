@@ -240,7 +240,9 @@ static void fam_grad(LargeState &S, double *g, const double *x) {
 }
 // cval = c(x); with Jout also the Jacobian (jac! writes both, autodiff_generators.jl:40-42)
 static void fam_c_jac(LargeState &S, double *Jout, double *cval, const double *x) {
-  if (Jout == S.J) S.jmap_valid = false;   // J is rewritten: its zero-slab map is stale until the next Gram scans it
+  // J is rewritten: its zero-slab map is stale until the next Gram scans it -- except for THOMSON, whose jac! kernel writes the
+  // same three structural entries of every row whatever x is (a map entry can then only be conservatively non-zero)
+  if (Jout == S.J && S.family != LFPSQP_FAM_THOMSON) S.jmap_valid = false;
   const int m = S.m;
   if (S.family == LFPSQP_FAM_HOST) {
     host_x(S, x);

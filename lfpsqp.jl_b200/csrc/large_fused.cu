@@ -58,6 +58,10 @@ struct FusedArgs {
   int rank, world;
   unsigned long long *epoch;
   unsigned *bar;             // grid-barrier arrival counter
+  // zero-slab map of J (large_gemm.cuh::zero_slab_map_kernel: 64 rows x 16 columns per byte) for the SKIP instantiation of the
+  // pcg! kernel: loads of all-zero slabs are not issued (same threads, same order: bit-identical to the dense streaming)
+  const unsigned char *nz = nullptr;
+  int64_t nz_ld = 0;
 };
 
 // ---- in-kernel all-reduce over NVLink: push model with flag-in-data mailboxes (the "LL" idea: every 16-byte entry
@@ -175,6 +179,7 @@ __device__ __forceinline__ void cta_sum_multi(double (&v)[NV], double *shm /* (F
 // over the whole phase and all CTAs finish together); v goes through double-buffered shared-memory chunks (one L2
 // read per CTA instead of one per row); CU x 128-bit loads in flight per lane.  Single GPU: t -> a.tm.  Column-sharded:
 // {partial t_i, exchange number e} is pushed into every rank's mailbox row [my rank] with one 128-bit store per peer.
+template <bool SKIP = false>
 __device__ __forceinline__ void fz_rows(const FusedArgs &a, const double *v, double2 *vch, bool multi, unsigned long long e) {
   const int G = gridDim.x, c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, m = a.m;
   const int64_t n2 = a.n >> 1;
@@ -183,6 +188,7 @@ __device__ __forceinline__ void fz_rows(const FusedArgs &a, const double *v, dou
     const int i = c + (pass0 * (FT / 32) + warp) * G;
     const bool act = i < m;
     const double *row = a.J + (int64_t)(act ? i : 0) * a.ldj;
+    const unsigned char *nzr = SKIP ? a.nz + (int64_t)((act ? i : 0) >> 6) * a.nz_ld : nullptr;
     const int nch = (int)((n2 + RCH - 1) / RCH);
     double acc = 0.0;
     __syncthreads();
@@ -202,7 +208,7 @@ __device__ __forceinline__ void fz_rows(const FusedArgs &a, const double *v, dou
         for (int p = lane; p < len; p += 32 * CU) {
           double2 q[CU];
 #pragma unroll
-          for (int k = 0; k < CU; k++) { const int pp = p + k * 32; q[k] = (pp < len) ? ld_stream2(rb + 2 * pp) : make_double2(0.0, 0.0); }
+          for (int k = 0; k < CU; k++) { const int pp = p + k * 32; q[k] = (pp < len && (!SKIP || nzr[(base + pp) >> 3])) ? ld_stream2(rb + 2 * pp) : make_double2(0.0, 0.0); }
           asm volatile("" ::: "memory");   // all CU loads are issued before the first shared-memory operand is fetched (bytes in flight)
 #pragma unroll
           for (int k = 0; k < CU; k++) { const int pp = p + k * 32; if (pp < len) { const double2 w = cur[pp]; acc += q[k].x * w.x + q[k].y * w.y; } }
@@ -221,7 +227,7 @@ __device__ __forceinline__ void fz_rows(const FusedArgs &a, const double *v, dou
 // ---- column phase shared by both kernels: s_j = sum_i J[i][j] u[i] over ALL m rows for the column pairs [p0, p1) this
 // CTA owns (u staged in shared memory `us`); thread groups split the rows, `fin(p, s0, s1)` is called once per pair by
 // its owner thread with the finished sums.
-template <class F>
+template <bool SKIP = false, class F>
 __device__ __forceinline__ void fz_cols(const FusedArgs &a, const double *us, double2 *red, int64_t p0, int64_t p1, F fin) {
   const int tid = threadIdx.x, m = a.m;
   for (int64_t pc = p0; pc < p1; pc += FT) {
@@ -231,16 +237,20 @@ __device__ __forceinline__ void fz_cols(const FusedArgs &a, const double *us, do
     double a0 = 0.0, a1 = 0.0;
     if (g < RG) {
       const double *base = a.J + 2 * (pc + pl);
+      const unsigned char *nzc = SKIP ? a.nz + ((pc + pl) >> 3) : nullptr;
       int i = g;
       for (; i + (CU - 1) * RG < m; i += CU * RG) {
         double2 q[CU];
 #pragma unroll
-        for (int k = 0; k < CU; k++) q[k] = ld_stream2(base + (int64_t)(i + k * RG) * a.ldj);
+        for (int k = 0; k < CU; k++) q[k] = (!SKIP || nzc[(int64_t)((i + k * RG) >> 6) * a.nz_ld]) ? ld_stream2(base + (int64_t)(i + k * RG) * a.ldj) : make_double2(0.0, 0.0);
         asm volatile("" ::: "memory");
 #pragma unroll
         for (int k = 0; k < CU; k++) { const double w = us[i + k * RG]; a0 += q[k].x * w; a1 += q[k].y * w; }
       }
-      for (; i < m; i += RG) { const double2 q = ld_stream2(base + (int64_t)i * a.ldj); const double w = us[i]; a0 += q.x * w; a1 += q.y * w; }
+      for (; i < m; i += RG) {
+        const double2 q = (!SKIP || nzc[(int64_t)(i >> 6) * a.nz_ld]) ? ld_stream2(base + (int64_t)i * a.ldj) : make_double2(0.0, 0.0);
+        const double w = us[i]; a0 += q.x * w; a1 += q.y * w;
+      }
     }
     __syncthreads();
     red[tid] = make_double2(a0, a1);
@@ -519,7 +529,7 @@ __global__ void __launch_bounds__(FT, 1) fused_projcg_kernel(FusedArgs a) {
 //   B   z = J' t + mu p ; partial p.z                                                            [owned columns]   (:222-226)
 //   B   alpha = rho / p.z ; dx += alpha p ; r -= alpha z ; partial r.r                           [owned columns]   (:229-235)
 //   B
-template <bool MULTI>
+template <bool MULTI, bool SKIP = false>
 __global__ void __launch_bounds__(FT, 1) fused_pcg_kernel(FusedArgs a) {
   __shared__ int s_abort;
   GridBar grid{a.bar, 0u, gridDim.x, MULTI ? a.abort_flag : nullptr, &s_abort};
@@ -560,7 +570,7 @@ __global__ void __launch_bounds__(FT, 1) fused_pcg_kernel(FusedArgs a) {
     if (grid.sync()) { status = 5; break; }
     if (exit_st) { status = exit_st; break; }
     // ---- t = J p
-    fz_rows(a, a.dc, vch, multi, ep + 1);
+    fz_rows<SKIP>(a, a.dc, vch, multi, ep + 1);
     if (grid.sync()) { status = 5; break; }
     if (multi) ++ep;
     // ---- z = J' t + mu p ; partial p.z
@@ -574,7 +584,7 @@ __global__ void __launch_bounds__(FT, 1) fused_pcg_kernel(FusedArgs a) {
       if (late) grid.raise();
       __syncthreads();
       double sp = 0.0;
-      fz_cols(a, fsm, reinterpret_cast<double2 *>(red_d), p0, p1, [&](int64_t p, double s0, double s1) {
+      fz_cols<SKIP>(a, fsm, reinterpret_cast<double2 *>(red_d), p0, p1, [&](int64_t p, double s0, double s1) {
         const double2 d2 = *reinterpret_cast<const double2 *>(a.dc + 2 * p);
         const double2 z2 = make_double2(s0 + mu * d2.x, s1 + mu * d2.y);
         *reinterpret_cast<double2 *>(a.Ad + 2 * p) = z2;
@@ -676,8 +686,11 @@ int fused_pcg(LargeState &S, double *dx, double *r, double *pv, double *z) {
   cudaMemsetAsync(a.bar, 0, 4 * sizeof(double), S.stream);   // barrier counter (+12) + abort flag (+14)
   const size_t smem = ((size_t)((S.m + 1) & ~1) + 2 * FT + 4 * RCH) * sizeof(double);
   void *args[] = {&a};
-  cudaError_t e = cudaLaunchCooperativeKernel(S.world > 1 ? (void *)fused_pcg_kernel<true> : (void *)fused_pcg_kernel<false>, dim3(S.fused_grid), dim3(FT),
-                                              args, smem, S.stream);
+  // block-sparse J whose zero-slab map is current (large.cu::gram_syrk): the instantiation that does not load all-zero slabs
+  const bool skip = S.world <= 1 && S.jmap_valid && S.gram_mode == 1 && S.nzmap;
+  if (skip) { a.nz = S.nzmap; a.nz_ld = S.nz_ld; }
+  void *kern = S.world > 1 ? (void *)fused_pcg_kernel<true> : (skip ? (void *)fused_pcg_kernel<false, true> : (void *)fused_pcg_kernel<false>);
+  cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3(S.fused_grid), dim3(FT), args, smem, S.stream);
   if (e != cudaSuccess) { cudaGetLastError(); return 1; }
   S.launches++;
   return 0;
@@ -693,7 +706,8 @@ void fused_projcg_init(LargeState &S, int device) {
   if (cudaFuncSetAttribute(fused_projcg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
       cudaFuncSetAttribute(fused_projcg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
       cudaFuncSetAttribute(fused_pcg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-      cudaFuncSetAttribute(fused_pcg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return; }
+      cudaFuncSetAttribute(fused_pcg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+      cudaFuncSetAttribute(fused_pcg_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return; }
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_projcg_kernel<true>, FT, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return; }
   S.fused_grid = S.sm_count;
