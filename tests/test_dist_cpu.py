@@ -91,3 +91,15 @@ def test_ranges_cover_and_balance():
             assert c[0][0] == 0 and sum(x[1] for x in c) == n and all(x[1] % 2 == 0 for x in c)
     with pytest.raises(Exception):
         D.column_range(7, 2, 0)
+    # Thomson shards whole points (3 coordinates each), an even number of them per rank
+    for npts in (2, 64, 4096, 4098):
+        for world in (1, 2, 4, 8):
+            if npts // 2 < world:
+                continue
+            c = [D.thomson_point_range(npts, world, k) for k in range(world)]
+            assert c[0][0] == 0 and sum(x[1] for x in c) == 3 * npts
+            assert all(x[1] % 6 == 0 and x[0] % 6 == 0 for x in c)                       # whole points, even count
+            assert all(c[i][0] + c[i][1] == c[i + 1][0] for i in range(world - 1))      # contiguous
+            assert max(x[1] for x in c) - min(x[1] for x in c) <= 6
+    with pytest.raises(Exception):
+        D.thomson_point_range(7, 2, 0)
